@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s (and march-steps/s) of the heightmap ray-march hot path at 4K on N B200s.
+
+Workload (BASELINE.json configs[3]): perspective 3840x2160 flythrough over a 16384^2
+synthetic fBm heightmap + colormap (csrc/synth_fbm.h, seed 1234), min_height 0, max_height 10, grid_width 0.01,
+step_dist 0.05, orbit camera frame n of 240: pos = (81.92 + 140 cos 2πt, -81.92 + 140 sin 2πt, 40), hang toward the
+map centre, vang 110°, hfov 90°.  One step = one full 4K frame per GPU; frames are sharded round-robin
+(frame = step*N + rank), maps replicated per GPU, no data-path collective (weak scaling).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload flythrough4k|...]
+
+Prints ONE JSON line (rank 0).  `value` is timed with CUDA events around K frames rendered into device memory
+(inputs resident in HBM); `e2e` times the same frames through the C-ABI call with a host output buffer (the D2H
+of the RGBA8 frame inside the timed region).  `--impl reference` times the UNMODIFIED reference
+(oracle/_ref/hmap_ref*, built from /root/reference by oracle/Makefile) on the host cores, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT), str(ROOT / "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+WORKLOADS = {
+    # name: (log2n, W, H, projection, step_dist, frames)
+    "flythrough4k": dict(log2n=14, W=3840, H=2160, projection=1, step_dist=0.05, frames=240,
+                         desc="perspective 3840x2160, 240-frame orbit over a 16384^2 fBm heightmap (BASELINE configs[3])"),
+    "spherical1080": dict(log2n=12, W=1920, H=1080, projection=2, step_dist=0.05, frames=240,
+                          desc="spherical 1920x1080 over a 4096^2 fBm heightmap (BASELINE configs[1])"),
+    "ortho4k": dict(log2n=13, W=3840, H=2160, projection=3, step_dist=0.00625, frames=240,
+                    desc="orthographic 3840x2160 over an 8192^2 fBm heightmap, step_dist/8 (BASELINE configs[2])"),
+    "smoke": dict(log2n=10, W=640, H=360, projection=1, step_dist=0.05, frames=240,
+                  desc="small debugging workload"),
+}
+GRID_WIDTH = 0.01
+MIN_HEIGHT, MAX_HEIGHT = 0.0, 10.0
+SEED = 1234
+REF_SAMPLE_DIV = 4          # the CPU arms render every frame at W/4 x H/4 (1/16 of the rays, same cameras)
+
+
+def camera(wl: dict, n: int) -> dict:
+    """Orbit camera of frame n (config-grammar values: degrees)."""
+    extent = (1 << wl["log2n"]) * GRID_WIDTH
+    cx, cy = extent / 2.0, -extent / 2.0
+    t = (n % wl["frames"]) / wl["frames"]
+    radius = extent * (140.0 / 163.84)
+    px, py = cx + radius * math.cos(2 * math.pi * t), cy + radius * math.sin(2 * math.pi * t)
+    hang_deg = math.degrees(math.atan2(cy - py, cx - px))
+    if wl["projection"] == 3:
+        return dict(pos=(px, py, 30.0), hang_deg=hang_deg, vang_deg=125.0, hfov_deg=90.0,
+                    ortho_width=extent * 1.2 / wl["W"])
+    return dict(pos=(px, py, 40.0 * extent / 163.84 + 10.0 * (1 - extent / 163.84)), hang_deg=hang_deg,
+                vang_deg=110.0, hfov_deg=90.0, ortho_width=0.03)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0: float, t1: float) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for (t, r) in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for (_, r) in self.rows]
+        sm, smax, reasons = [], [], set()
+        for r in rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms: the unmodified reference (oracle/_ref) or, if it was not built, the oracle port
+# ------------------------------------------------------------------------------------------------
+def run_cpu_reference(wl: dict, frame_ids: list[int], warmup: int, workdir: Path) -> dict:
+    """Times frames `frame_ids` at (W/4 x H/4) on the host cores.  Returns dict with per-frame ms, rays, kind."""
+    import numpy as np
+
+    import oracle_lib as O
+
+    W, H = wl["W"] // REF_SAMPLE_DIV, wl["H"] // REF_SAMPLE_DIV
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    hm, cm = O.synth_maps(wl["log2n"], SEED)
+    gen_s = time.perf_counter() - t0
+    sample = f"{len(frame_ids)} frames of the workload's camera path at {W}x{H} (every {REF_SAMPLE_DIV}th ray per axis)"
+
+    if O.REF_BIN_O2.exists() and O.REF_BIN.exists():
+        hp, cp = workdir / "height.pgm", workdir / "color.tga"
+        with open(hp, "wb") as f:
+            f.write(b"P5\n%d %d\n255\n" % (hm.shape[1], hm.shape[0]))
+            f.write(np.ascontiguousarray(hm[:, :, 0]).tobytes())
+        O.write_tga_rgba(cp, cm)
+        cams = [camera(wl, n) for n in ([frame_ids[0]] * warmup + frame_ids)]
+        kw = dict(width=W, height=H, grid_width=GRID_WIDTH, step_dist=wl["step_dist"], min_height=MIN_HEIGHT,
+                  max_height=MAX_HEIGHT, **cams[0])
+        cfg = O.config_text(kw, hp, cp)
+        script = ["pos %r %r %r hang %r vang %r ortho_width %r" % (*c["pos"], c["hang_deg"], c["vang_deg"], c["ortho_width"])
+                  for c in cams]
+        out = {}
+        for label, binary in (("O2", O.REF_BIN_O2), ("as_shipped", O.REF_BIN)):
+            frames, times = O.run_ref(cfg, wl["projection"], W, H, script=script, binary=binary, threads=cores,
+                                      timeout=3000)
+            out[label] = dict(ms=times[warmup:], frames=frames[warmup:])
+        return dict(kind="reference", cores=cores, sample=sample, W=W, H=H, ms=out["O2"]["ms"],
+                    ms_as_shipped=out["as_shipped"]["ms"], frames=out["O2"]["frames"], gen_s=gen_s,
+                    binary="oracle/_ref/hmap_ref_O2 (reference sources + -O2; as shipped = no -O, also timed)")
+
+    # port: the plain-C restatement, OpenMP over all cores
+    heights = O.update_heightmap(hm, (0.299, 0.587, 0.114), MIN_HEIGHT, MAX_HEIGHT)
+    ms, frames = [], []
+    for i, n in enumerate([frame_ids[0]] * warmup + frame_ids):
+        c = camera(wl, n)
+        fr = O.make_frame(projection=wl["projection"], width=W, height=H, grid_width=GRID_WIDTH,
+                          step_dist=wl["step_dist"], min_height=MIN_HEIGHT, max_height=MAX_HEIGHT, **c)
+        t0 = time.perf_counter()
+        fb, _, _ = O.render(fr, heights, cm, want_steps=False)
+        dt = (time.perf_counter() - t0) * 1e3
+        if i >= warmup:
+            ms.append(dt)
+            frames.append(fb)
+    return dict(kind="port", cores=cores, sample=sample, W=W, H=H, ms=ms, ms_as_shipped=None, frames=frames,
+                gen_s=gen_s, binary="oracle/_build/liboracle.so (gcc -O2 -fopenmp)")
+
+
+def reference_arm(args, wl) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frame_ids = [(s * args.gpus) % wl["frames"] for s in range(args.steps)]
+    with tempfile.TemporaryDirectory(prefix="hmrm_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+        res = run_cpu_reference(wl, frame_ids, args.warmup, Path(td))
+    rays = res["W"] * res["H"]
+    total_ms = sum(res["ms"])
+    value = rays * len(res["ms"]) / (total_ms * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / len(res["ms"]),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "sample": res["sample"]},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": res["cores"], "kind": res["kind"],
+                         "sample": res["sample"], "binary": res["binary"]},
+        "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    if res["ms_as_shipped"]:
+        line["cpu_baseline"]["value_as_shipped"] = rays * len(res["ms_as_shipped"]) / (sum(res["ms_as_shipped"]) * 1e-3) / 1e6
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def ours_arm(args, wl) -> None:
+    import numpy as np
+    import torch
+
+    import hmrm_pkg
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    hmrm = hmrm_pkg.load()
+    from heightmap_ray_marcher_b200 import binding
+
+    r = hmrm.Renderer(local)
+    r.min_height, r.max_height = MIN_HEIGHT, MAX_HEIGHT
+    r.synth_maps(wl["log2n"], SEED)
+    W, H = wl["W"], wl["H"]
+    traversal = {"auto": 0, "brute": 1, "skip": 2}[args.traversal]
+
+    def frame_of(n: int, flags: int = 0, w: int = W, h: int = H):
+        c = camera(wl, n)
+        return r.frame(projection=wl["projection"], screen_width=w, screen_height=h, cam_pos=c["pos"],
+                       hang=hmrm.deg2rad(c["hang_deg"]), vang=hmrm.deg2rad(c["vang_deg"]),
+                       hfov=hmrm.deg2rad(c["hfov_deg"]), ortho_width=c["ortho_width"], grid_width=GRID_WIDTH,
+                       step_dist=wl["step_dist"], traversal=traversal, flags=flags)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    my_frames = [(s * world + rank) % wl["frames"] for s in range(args.steps)]
+    warm_frames = [((args.steps + s) * world + rank) % wl["frames"] for s in range(args.warmup)]
+    d_out = torch.empty((H, W, 4), dtype=torch.uint8, device=f"cuda:{local}")
+    h_out = binding.pinned_empty((H, W, 4))
+    stream = torch.cuda.current_stream()
+
+    # ---- untimed statistics pass over the timed frames: reference-equivalent steps S, hits, fetches ----
+    S = hits = fetches = 0
+    for n in my_frames:
+        r.render_device(frame_of(n, flags=hmrm.FLAG_STATS), d_out, stream.cuda_stream)
+        st = r.stats()
+        S += st.steps
+        hits += st.surf_hits
+        fetches += st.fetches
+        if st.status:
+            raise SystemExit(f"frame {n}: kernel reported status {st.status}")
+
+    # ---- value: K frames, device-resident, CUDA events on the launching stream ----
+    for n in warm_frames:
+        r.render_device(frame_of(n), d_out, stream.cuda_stream)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    for n in my_frames:
+        r.render_device(frame_of(n), d_out, stream.cuda_stream)
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    dev_ms = ev0.elapsed_time(ev1)
+
+    # ---- e2e: the user's call — host output buffer, D2H inside the timed region ----
+    for n in warm_frames:
+        r.render(frame_of(n), out=h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for n in my_frames:
+        r.render(frame_of(n), out=h_out)
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    clocks = sampler.stop(t_wall0, time.perf_counter()) if rank == 0 else None
+
+    # ---- per-kernel duration for the roofline: CUDA events around K2 inside the library ----
+    kernel_ms = []
+    for n in my_frames:
+        r.render_device(frame_of(n), d_out, stream.cuda_stream)
+        kernel_ms.append(r.stats().kernel_ms)
+
+    vals = torch.tensor([dev_ms, e2e_ms, float(S), float(hits), float(fetches), sum(kernel_ms)], dtype=torch.float64,
+                        device=f"cuda:{local}")
+    if dist is not None:
+        mx = vals.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vals.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms, e2e_ms = float(mx[0]), float(mx[1])
+        S, hits, fetches = int(sm[2]), int(sm[3]), int(sm[4])
+        k_ms_total = float(sm[5]) / world
+    else:
+        k_ms_total = sum(kernel_ms)
+
+    if rank == 0:
+        rays_total = W * H * args.steps * world
+        value = rays_total / (dev_ms * 1e-3) / 1e6
+        e2e_value = rays_total / (e2e_ms * 1e-3) / 1e6
+        # algorithmic bytes: 8 B per reference step + 4 B colormap per hit + 4 B store per pixel
+        alg_bytes = 8 * S + 4 * hits + 4 * rays_total
+        launches = args.steps * world
+        k_ms = k_ms_total / args.steps            # average K2 duration on one GPU
+        achieved = (alg_bytes / launches) / (k_ms * 1e-3) / 1e9
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            traffic = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(args.workload)
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "desc": wl["desc"], "traversal": args.traversal,
+                       "precision": "fp64_exact", "sharding": f"frames round-robin over {world} GPU(s), maps replicated",
+                       "l2": "inputs larger than L2 (2 GiB FP64 height plane + 1 GiB RGBA8 colormap per GPU; "
+                             "the camera moves every frame)" if wl["log2n"] >= 13 else "inputs may fit L2; camera moves every frame"},
+            "march_steps_per_s": S / (dev_ms * 1e-3), "ref_steps_per_frame": S / (args.steps * world),
+            "fetches_per_frame": fetches / (args.steps * world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
+                         "peak_source": "measured" if "hbm_gbs" in peaks else "fallback", "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "kernel": "k2_render", "kernel_ms": k_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes / launches,
+                         "note": "algorithmic bytes = 8*S + 4*hits + 4*W*H with S = reference-equivalent steps"},
+            "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": W * H * 4},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            with tempfile.TemporaryDirectory(prefix="hmrm_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
+                res = run_cpu_reference(wl, my_frames[:args.cpu_frames], 1, Path(td))
+            cpu_rays = res["W"] * res["H"] * len(res["ms"])
+            cb = {"value": cpu_rays / (sum(res["ms"]) * 1e-3) / 1e6, "unit": "Mrays/s", "cores": res["cores"],
+                  "kind": res["kind"], "sample": res["sample"], "binary": res["binary"]}
+            if res["ms_as_shipped"]:
+                cb["value_as_shipped"] = cpu_rays / (sum(res["ms_as_shipped"]) * 1e-3) / 1e6
+            # parity of the sampled frames: GPU render at the sample resolution == CPU frame, bit for bit
+            ok = True
+            for n, want in zip(my_frames[:args.cpu_frames], res["frames"]):
+                got = r.render(frame_of(n, w=res["W"], h=res["H"]))
+                ok = ok and bool(np.array_equal(got, want))
+            cb["parity_of_sample"] = "bit-exact" if ok else "MISMATCH"
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+
+    r.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", choices=sorted(WORKLOADS), default="flythrough4k")
+    ap.add_argument("--traversal", choices=["auto", "brute", "skip"], default="auto")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=2)
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        reference_arm(args, wl)
+    else:
+        ours_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,55 @@
+"""Build libhmrm.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+
+    python heightmap-ray-marcher_b200/build.py [--force]
+
+nvcc cross-compiles without a GPU; the resulting .so is git-ignored but travels
+to the GPU box with the repository snapshot.
+"""
+from __future__ import annotations
+
+import subprocess
+import sys
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libhmrm.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",                      # exact mode: no FMA contraction anywhere (north star)
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-Wall",
+    "-shared",
+]
+
+
+def sources() -> list[Path]:
+    return sorted(CSRC.glob("*.cu"))
+
+
+def deps() -> list[Path]:
+    return sorted(list(CSRC.glob("*")) + [PKG.parent / "include" / "hmrm.h", Path(__file__)])
+
+
+def is_stale() -> bool:
+    if not LIB.exists():
+        return True
+    t = LIB.stat().st_mtime
+    return any(p.stat().st_mtime > t for p in deps())
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> Path:
+    if not force and not is_stale():
+        return LIB
+    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB), *[str(s) for s in sources()]]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+        print(" ".join(cmd))
+    subprocess.run(cmd, check=True, cwd=str(PKG))
+    return LIB
+
+
+if __name__ == "__main__":
+    build_lib(force="--force" in sys.argv, verbose=True)
+    print(LIB)

@@ -1,0 +1,658 @@
+// libhmrm.so — C ABI (include/hmrm.h) over the sm_100a kernels.
+//
+// Host responsibilities (the reference does these inline in main(), see the
+// line references in include/hmrm.h): own the device copies of the maps, run
+// the K1 prepass when lum/min/max/maps change, build the per-frame image-plane
+// constants with the host libm, launch K2, move the framebuffer.
+// There is no CPU rendering path in this library.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/hmrm.h"
+#include "frame_setup.h"
+#include "k1_prepass.cuh"
+#include "k2_render_brute.cuh"
+#include "render_params.h"
+#include "synth_fbm.h"
+
+using namespace hmrm;
+
+namespace {
+
+std::string g_create_error;
+
+struct Staging {
+	double *host;          // pinned
+	size_t cap;            // doubles
+	cudaEvent_t consumed;  // recorded after the H2D copy that reads `host`
+	bool pending;
+};
+
+} // namespace
+
+struct hmrm_ctx {
+	int device;
+	int num_sms;
+	cudaStream_t stream;
+	cudaEvent_t ev_begin, ev_end;
+	std::string err;
+
+	// maps
+	int map_w, map_h;
+	uint8_t *d_rgb;              // RGB8 [map_h][map_w][3]
+	uint32_t *d_color;           // RGBA8
+	double *d_surf;              // fl(height + min_height)
+	unsigned long long *d_max_bits;
+	bool maps_set, heights_set;
+	double lum[3], min_height, max_height, max_surf;
+
+	// per-resolution tables
+	int tab_w, tab_h;
+	std::vector<double> wtab, htab, sph;
+	double *d_wtab, *d_htab, *d_sph;
+	size_t sph_cap;
+	Staging staging[2];
+	int staging_next;
+
+	// outputs
+	uint32_t *d_fb;
+	int fb_w, fb_h;
+	int32_t *d_step_index;
+	size_t step_index_cap;
+	DeviceStats *d_stats;
+	unsigned int *d_tile_counter;
+	bool last_had_stats, last_had_step_index, timing_valid;
+	int last_w, last_h;
+};
+
+namespace {
+
+int fail(hmrm_ctx *ctx, int code, const char *fmt, ...) {
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	if (ctx) ctx->err = buf;
+	else g_create_error = buf;
+	return code;
+}
+
+#define HMRM_CUDA(ctx, call)                                                                       \
+	do {                                                                                           \
+		cudaError_t e_ = (call);                                                                   \
+		if (e_ != cudaSuccess)                                                                     \
+			return fail((ctx), HMRM_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));     \
+	} while (0)
+
+bool finite3(const double *v) { return std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]); }
+
+__global__ void __launch_bounds__(256) k_synth_maps(uint32_t log2n, uint32_t seed, uint8_t *__restrict__ rgb,
+                                                    uint32_t *__restrict__ rgba) {
+	const uint32_t n = 1u << log2n;
+	const unsigned long long total = (unsigned long long)n * n;
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (unsigned long long p = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += stride) {
+		const uint32_t x = (uint32_t)(p & (n - 1u)), y = (uint32_t)(p >> log2n);
+		const uint32_t v = hmrm_synth_height(x, y, log2n, seed);
+		rgb[3ULL * p + 0] = (uint8_t)v;
+		rgb[3ULL * p + 1] = (uint8_t)v;
+		rgb[3ULL * p + 2] = (uint8_t)v;
+		rgba[p] = hmrm_synth_color(v, x, y, n);
+	}
+}
+
+void free_maps(hmrm_ctx *c) {
+	cudaFree(c->d_rgb);
+	cudaFree(c->d_color);
+	cudaFree(c->d_surf);
+	c->d_rgb = NULL;
+	c->d_color = NULL;
+	c->d_surf = NULL;
+	c->maps_set = c->heights_set = false;
+}
+
+int alloc_maps(hmrm_ctx *c, int32_t w, int32_t h) {
+	if (w < 1 || h < 1) return fail(c, HMRM_ERR_INVALID, "map size %dx%d is not positive", w, h);
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	if (c->maps_set && c->map_w == w && c->map_h == h) {
+		c->heights_set = false;
+		return HMRM_OK;
+	}
+	free_maps(c);
+	const size_t n = (size_t)w * (size_t)h;
+	HMRM_CUDA(c, cudaMalloc(&c->d_rgb, n * 3));
+	HMRM_CUDA(c, cudaMalloc(&c->d_color, n * 4));
+	HMRM_CUDA(c, cudaMalloc(&c->d_surf, n * 8));
+	c->map_w = w;
+	c->map_h = h;
+	return HMRM_OK;
+}
+
+int ensure_tables(hmrm_ctx *c, int W, int H) {
+	if (c->tab_w == W && c->tab_h == H) return HMRM_OK;
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_wtab);
+	cudaFree(c->d_htab);
+	c->d_wtab = c->d_htab = NULL;
+	c->tab_w = c->tab_h = 0;
+	fill_wh_tables(W, H, &c->wtab, &c->htab);
+	HMRM_CUDA(c, cudaMalloc(&c->d_wtab, (size_t)W * 8));
+	HMRM_CUDA(c, cudaMalloc(&c->d_htab, (size_t)H * 8));
+	HMRM_CUDA(c, cudaMemcpy(c->d_wtab, c->wtab.data(), (size_t)W * 8, cudaMemcpyHostToDevice));
+	HMRM_CUDA(c, cudaMemcpy(c->d_htab, c->htab.data(), (size_t)H * 8, cudaMemcpyHostToDevice));
+	const size_t need = (size_t)(2 * W + 2 * H);
+	if (need > c->sph_cap) {
+		cudaFree(c->d_sph);
+		c->d_sph = NULL;
+		HMRM_CUDA(c, cudaMalloc(&c->d_sph, need * 8));
+		for (int i = 0; i < 2; ++i) {
+			if (c->staging[i].host) cudaFreeHost(c->staging[i].host);
+			c->staging[i].host = NULL;
+			HMRM_CUDA(c, cudaMallocHost(&c->staging[i].host, need * 8));
+			c->staging[i].cap = need;
+			c->staging[i].pending = false;
+		}
+		c->sph_cap = need;
+	}
+	c->tab_w = W;
+	c->tab_h = H;
+	return HMRM_OK;
+}
+
+int ensure_framebuffer(hmrm_ctx *c, int W, int H) {
+	if (c->d_fb && c->fb_w == W && c->fb_h == H) return HMRM_OK;
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_fb);
+	c->d_fb = NULL;
+	HMRM_CUDA(c, cudaMalloc(&c->d_fb, (size_t)W * (size_t)H * 4));
+	// the reference's framebuf starts uninitialised (main/hmap.cpp:612); start from zeros instead
+	HMRM_CUDA(c, cudaMemset(c->d_fb, 0, (size_t)W * (size_t)H * 4));
+	c->fb_w = W;
+	c->fb_h = H;
+	return HMRM_OK;
+}
+
+int validate_frame(hmrm_ctx *c, const hmrm_frame *f, int *row_begin, int *row_end) {
+	if (!f) return fail(c, HMRM_ERR_INVALID, "frame is NULL");
+	if (!c->maps_set) return fail(c, HMRM_ERR_STATE, "hmrm_set_maps has not been called");
+	if (!c->heights_set) return fail(c, HMRM_ERR_STATE, "hmrm_update_heightmap has not been called");
+	if (f->projection < HMRM_PERSPECTIVE || f->projection > HMRM_ORTHOGRAPHIC)
+		return fail(c, HMRM_ERR_INVALID, "projection %d is not 1, 2 or 3", f->projection);
+	// w = px/(W-1), h = py/(H-1) (main/hmap.cpp:986-987) are 0/0 for a 1-pixel axis
+	if (f->screen_width < 2 || f->screen_height < 2 || f->screen_width > 65536 || f->screen_height > 65536)
+		return fail(c, HMRM_ERR_INVALID, "resolution %dx%d outside [2,65536]", f->screen_width, f->screen_height);
+	if (!finite3(f->cam_pos) || !std::isfinite(f->hang) || !std::isfinite(f->vang) || !std::isfinite(f->hfov) ||
+	    !std::isfinite(f->ortho_width))
+		return fail(c, HMRM_ERR_INVALID, "camera parameters must be finite");
+	if (!(f->grid_width > 0.0) || !std::isfinite(f->grid_width))
+		return fail(c, HMRM_ERR_INVALID, "grid_width must be positive and finite");
+	// step_dist <= 0 never terminates in the reference (main/hmap.cpp:1000-1038)
+	if (!(f->step_dist > 0.0) || !std::isfinite(f->step_dist))
+		return fail(c, HMRM_ERR_INVALID, "step_dist must be positive and finite");
+	// cycle_period 0 is a division by zero in the reference (main/hmap.cpp:976)
+	if (f->cycle_period < 1 || f->cycle < 0 || f->cycle >= f->cycle_period)
+		return fail(c, HMRM_ERR_INVALID, "need cycle_period >= 1 and 0 <= cycle < cycle_period");
+	if (f->precision != HMRM_FP64_EXACT && f->precision != HMRM_FP32_FAST)
+		return fail(c, HMRM_ERR_INVALID, "unknown precision %d", f->precision);
+	int rb = f->row_begin, re = f->row_end;
+	if (rb == 0 && re == 0) re = f->screen_height;
+	if (rb < 0 || re > f->screen_height || rb >= re)
+		return fail(c, HMRM_ERR_INVALID, "row band [%d,%d) outside the frame", rb, re);
+	*row_begin = rb;
+	*row_end = re;
+	return HMRM_OK;
+}
+
+// Enqueue one frame on `stream`, writing RGBA8 into d_out.
+int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream_t stream, bool timed) {
+	int row_begin = 0, row_end = 0;
+	int rc = validate_frame(c, f, &row_begin, &row_end);
+	if (rc) return rc;
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	const int W = f->screen_width, H = f->screen_height;
+	if ((rc = ensure_tables(c, W, H)) != HMRM_OK) return rc;
+
+	const PlaneConst pc = build_plane(*f);
+
+	RenderParams P;
+	std::memset(&P, 0, sizeof P);
+	P.projection = f->projection;
+	P.W = W;
+	P.H = H;
+	P.row_begin = row_begin;
+	P.row_end = row_end;
+	P.cycle = f->cycle;
+	P.period = f->cycle_period;
+	P.tiles_x = (W + 7) / 8;
+	P.tiles_y = (row_end - row_begin + 3) / 4;
+	P.map_w = c->map_w;
+	P.map_h = c->map_h;
+	const Vec3 *src[5] = {&pc.cam, &pc.ul, &pc.pr, &pc.pd, &pc.look};
+	double *dst[5] = {P.cam, P.ul, P.pr, P.pd, P.look};
+	for (int i = 0; i < 5; ++i) {
+		dst[i][0] = src[i]->x;
+		dst[i][1] = src[i]->y;
+		dst[i][2] = src[i]->z;
+	}
+	// main/hmap.cpp:967-974
+	P.c0[0] = 0.0;
+	P.c0[1] = 0.0;
+	P.c0[2] = c->min_height;
+	P.c1[0] = P.c0[0] + c->map_w * f->grid_width;
+	P.c1[1] = P.c0[1] - c->map_h * f->grid_width;
+	P.c1[2] = c->max_height;
+	P.gw = f->grid_width;
+	P.nudge = f->grid_width * 0.01;
+	P.step_dist = f->step_dist;
+	P.max_surf = c->max_surf;
+	P.wtab = c->d_wtab;
+	P.htab = c->d_htab;
+
+	if (f->projection == HMRM_SPHERICAL) {
+		Staging &st = c->staging[c->staging_next];
+		c->staging_next ^= 1;
+		if (st.pending) {
+			HMRM_CUDA(c, cudaEventSynchronize(st.consumed));
+			st.pending = false;
+		}
+		fill_spherical_tables(pc, W, H, c->wtab, c->htab, &c->sph);
+		std::memcpy(st.host, c->sph.data(), c->sph.size() * 8);
+		HMRM_CUDA(c, cudaMemcpyAsync(c->d_sph, st.host, c->sph.size() * 8, cudaMemcpyHostToDevice, stream));
+		HMRM_CUDA(c, cudaEventRecord(st.consumed, stream));
+		st.pending = true;
+		P.cos_ha = c->d_sph;
+		P.sin_ha = c->d_sph + W;
+		P.sin_va = c->d_sph + 2 * W;
+		P.cos_va = c->d_sph + 2 * W + H;
+	}
+
+	P.surf = c->d_surf;
+	P.color = c->d_color;
+	P.fb = d_out;
+	P.bg[0] = f->bg[0];
+	P.bg[1] = f->bg[1];
+	P.bg[2] = f->bg[2];
+	P.bg_rgba = (uint32_t)f->bg[0] | ((uint32_t)f->bg[1] << 8) | ((uint32_t)f->bg[2] << 16) | 0xFF000000u;
+
+	const bool want_stats = (f->flags & HMRM_FLAG_STATS) != 0;
+	const bool want_steps = (f->flags & HMRM_FLAG_STEP_INDEX) != 0;
+	if (want_steps) {
+		const size_t need = (size_t)W * (size_t)H;
+		if (need > c->step_index_cap) {
+			HMRM_CUDA(c, cudaStreamSynchronize(stream));
+			cudaFree(c->d_step_index);
+			c->d_step_index = NULL;
+			HMRM_CUDA(c, cudaMalloc(&c->d_step_index, need * 4));
+			c->step_index_cap = need;
+		}
+		HMRM_CUDA(c, cudaMemsetAsync(c->d_step_index, 0xFD, need * 4, stream));   // -3 = not rendered... bytes FD
+		P.step_index = c->d_step_index;
+	}
+	P.stats = c->d_stats;
+	P.tile_counter = c->d_tile_counter;
+
+	HMRM_CUDA(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int), stream));
+	HMRM_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), stream));
+
+	const int n_tiles = P.tiles_x * P.tiles_y;
+	const int warps_per_block = 8;
+	int blocks = c->num_sms * 8;   // 64 resident warps per SM at <= 32 registers... capped by occupancy anyway
+	const int max_useful = (n_tiles + warps_per_block - 1) / warps_per_block;
+	if (blocks > max_useful) blocks = max_useful;
+	if (blocks < 1) blocks = 1;
+
+	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_begin, stream));
+	if (want_stats) k2_render_brute<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+	else k2_render_brute<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+	HMRM_CUDA(c, cudaGetLastError());
+	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_end, stream));
+
+	c->last_had_stats = want_stats;
+	c->last_had_step_index = want_steps;
+	c->timing_valid = timed;
+	c->last_w = W;
+	c->last_h = H;
+	return HMRM_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int hmrm_abi_version(void) { return HMRM_ABI_VERSION; }
+
+int hmrm_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+	return n;
+}
+
+const char *hmrm_last_error(const hmrm_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hmrm_create(int device, hmrm_ctx **out) {
+	if (!out) return fail(NULL, HMRM_ERR_INVALID, "out is NULL");
+	*out = NULL;
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0)
+		return fail(NULL, HMRM_ERR_CUDA, "no CUDA device available (%s); this library has no CPU path",
+		            e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+	if (device < 0 || device >= n) return fail(NULL, HMRM_ERR_INVALID, "device %d not in [0,%d)", device, n);
+	HMRM_CUDA(NULL, cudaSetDevice(device));
+	cudaDeviceProp prop;
+	HMRM_CUDA(NULL, cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+		return fail(NULL, HMRM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+		            prop.major, prop.minor);
+
+	hmrm_ctx *c = new hmrm_ctx();
+	c->device = device;
+	c->num_sms = prop.multiProcessorCount;
+	c->stream = NULL;
+	c->map_w = c->map_h = 0;
+	c->d_rgb = NULL;
+	c->d_color = NULL;
+	c->d_surf = NULL;
+	c->d_max_bits = NULL;
+	c->maps_set = c->heights_set = false;
+	c->lum[0] = 0.299;
+	c->lum[1] = 0.587;
+	c->lum[2] = 0.114;
+	c->min_height = 0.0;
+	c->max_height = 10.0;
+	c->max_surf = 0.0;
+	c->tab_w = c->tab_h = 0;
+	c->d_wtab = c->d_htab = c->d_sph = NULL;
+	c->sph_cap = 0;
+	for (int i = 0; i < 2; ++i) {
+		c->staging[i].host = NULL;
+		c->staging[i].cap = 0;
+		c->staging[i].pending = false;
+		c->staging[i].consumed = NULL;
+	}
+	c->staging_next = 0;
+	c->d_fb = NULL;
+	c->fb_w = c->fb_h = 0;
+	c->d_step_index = NULL;
+	c->step_index_cap = 0;
+	c->d_stats = NULL;
+	c->d_tile_counter = NULL;
+	c->last_had_stats = c->last_had_step_index = c->timing_valid = false;
+	c->last_w = c->last_h = 0;
+
+	cudaError_t err = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (err == cudaSuccess) err = cudaEventCreate(&c->ev_begin);
+	if (err == cudaSuccess) err = cudaEventCreate(&c->ev_end);
+	for (int i = 0; i < 2 && err == cudaSuccess; ++i)
+		err = cudaEventCreateWithFlags(&c->staging[i].consumed, cudaEventDisableTiming);
+	if (err == cudaSuccess) err = cudaMalloc(&c->d_stats, sizeof(DeviceStats));
+	if (err == cudaSuccess) err = cudaMalloc(&c->d_tile_counter, 256);
+	if (err == cudaSuccess) err = cudaMalloc(&c->d_max_bits, 8);
+	if (err != cudaSuccess) {
+		fail(NULL, HMRM_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));
+		hmrm_destroy(c);
+		return HMRM_ERR_CUDA;
+	}
+	*out = c;
+	return HMRM_OK;
+}
+
+void hmrm_destroy(hmrm_ctx *c) {
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	free_maps(c);
+	cudaFree(c->d_max_bits);
+	cudaFree(c->d_wtab);
+	cudaFree(c->d_htab);
+	cudaFree(c->d_sph);
+	for (int i = 0; i < 2; ++i) {
+		if (c->staging[i].host) cudaFreeHost(c->staging[i].host);
+		if (c->staging[i].consumed) cudaEventDestroy(c->staging[i].consumed);
+	}
+	cudaFree(c->d_fb);
+	cudaFree(c->d_step_index);
+	cudaFree(c->d_stats);
+	cudaFree(c->d_tile_counter);
+	if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+	if (c->ev_end) cudaEventDestroy(c->ev_end);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int hmrm_set_maps(hmrm_ctx *c, const uint8_t *height_rgb8, const uint8_t *color_rgba8, int32_t w, int32_t h) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!height_rgb8 || !color_rgba8) return fail(c, HMRM_ERR_INVALID, "map pointers must not be NULL");
+	int rc = alloc_maps(c, w, h);
+	if (rc) return rc;
+	const size_t n = (size_t)w * (size_t)h;
+	HMRM_CUDA(c, cudaMemcpyAsync(c->d_rgb, height_rgb8, n * 3, cudaMemcpyHostToDevice, c->stream));
+	HMRM_CUDA(c, cudaMemcpyAsync(c->d_color, color_rgba8, n * 4, cudaMemcpyHostToDevice, c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->maps_set = true;
+	return HMRM_OK;
+}
+
+int hmrm_set_maps_device(hmrm_ctx *c, const void *d_rgb8, const void *d_rgba8, int32_t w, int32_t h) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!d_rgb8 || !d_rgba8) return fail(c, HMRM_ERR_INVALID, "map pointers must not be NULL");
+	int rc = alloc_maps(c, w, h);
+	if (rc) return rc;
+	const size_t n = (size_t)w * (size_t)h;
+	HMRM_CUDA(c, cudaMemcpyAsync(c->d_rgb, d_rgb8, n * 3, cudaMemcpyDeviceToDevice, c->stream));
+	HMRM_CUDA(c, cudaMemcpyAsync(c->d_color, d_rgba8, n * 4, cudaMemcpyDeviceToDevice, c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->maps_set = true;
+	return HMRM_OK;
+}
+
+int hmrm_synth_maps(hmrm_ctx *c, uint32_t log2n, uint32_t seed) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (log2n < 4 || log2n > 15) return fail(c, HMRM_ERR_INVALID, "log2n %u outside [4,15]", log2n);
+	const int32_t n = (int32_t)(1u << log2n);
+	int rc = alloc_maps(c, n, n);
+	if (rc) return rc;
+	k_synth_maps<<<c->num_sms * 8, 256, 0, c->stream>>>(log2n, seed, c->d_rgb, c->d_color);
+	HMRM_CUDA(c, cudaGetLastError());
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->maps_set = true;
+	return HMRM_OK;
+}
+
+int hmrm_get_maps(hmrm_ctx *c, uint8_t *height_rgb8, uint8_t *color_rgba8) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!c->maps_set) return fail(c, HMRM_ERR_STATE, "maps not set");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	const size_t n = (size_t)c->map_w * (size_t)c->map_h;
+	if (height_rgb8) HMRM_CUDA(c, cudaMemcpyAsync(height_rgb8, c->d_rgb, n * 3, cudaMemcpyDeviceToHost, c->stream));
+	if (color_rgba8) HMRM_CUDA(c, cudaMemcpyAsync(color_rgba8, c->d_color, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	return HMRM_OK;
+}
+
+int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, double max_height) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!c->maps_set) return fail(c, HMRM_ERR_STATE, "hmrm_set_maps has not been called");
+	if (!lum || !finite3(lum) || !std::isfinite(min_height) || !std::isfinite(max_height))
+		return fail(c, HMRM_ERR_INVALID, "lum, min_height and max_height must be finite");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	PrepassParams q;
+	q.lum_r = lum[0];
+	q.lum_g = lum[1];
+	q.lum_b = lum[2];
+	q.min_height = min_height;
+	q.span = max_height - min_height;
+	const long long n = (long long)c->map_w * c->map_h;
+	HMRM_CUDA(c, cudaMemsetAsync(c->d_max_bits, 0, 8, c->stream));
+	k1_prepass<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, n, q, c->d_surf, NULL, c->d_max_bits);
+	HMRM_CUDA(c, cudaGetLastError());
+	unsigned long long bits = 0;
+	HMRM_CUDA(c, cudaMemcpyAsync(&bits, c->d_max_bits, 8, cudaMemcpyDeviceToHost, c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->max_surf = from_ordered_bits(bits);
+	c->lum[0] = lum[0];
+	c->lum[1] = lum[1];
+	c->lum[2] = lum[2];
+	c->min_height = min_height;
+	c->max_height = max_height;
+	c->heights_set = true;
+	return HMRM_OK;
+}
+
+int hmrm_get_heights(hmrm_ctx *c, double *heights) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!heights) return fail(c, HMRM_ERR_INVALID, "heights is NULL");
+	if (!c->heights_set) return fail(c, HMRM_ERR_STATE, "hmrm_update_heightmap has not been called");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	const long long n = (long long)c->map_w * c->map_h;
+	double *d_tmp = NULL;
+	HMRM_CUDA(c, cudaMalloc(&d_tmp, (size_t)n * 8));
+	PrepassParams q;
+	q.lum_r = c->lum[0];
+	q.lum_g = c->lum[1];
+	q.lum_b = c->lum[2];
+	q.min_height = c->min_height;
+	q.span = c->max_height - c->min_height;
+	k1_prepass<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, n, q, NULL, d_tmp, NULL);
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaMemcpyAsync(heights, d_tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_tmp);
+	if (e != cudaSuccess) return fail(c, HMRM_ERR_CUDA, "hmrm_get_heights: %s", cudaGetErrorString(e));
+	return HMRM_OK;
+}
+
+void hmrm_frame_defaults(hmrm_frame *f) {
+	if (!f) return;
+	std::memset(f, 0, sizeof *f);
+	f->projection = HMRM_PERSPECTIVE;     // main/hmap.cpp:107
+	f->screen_width = 800;                // :31
+	f->screen_height = 600;               // :32
+	f->precision = HMRM_FP64_EXACT;
+	f->cam_pos[0] = -5.0;                 // :75
+	f->cam_pos[1] = 5.0;
+	f->cam_pos[2] = 0.0;
+	f->hang = -M_PI / 4.0;                // :80
+	f->vang = M_PI / 2.0;                 // :85
+	f->hfov = M_PI / 2.0;                 // :35
+	f->grid_width = 0.05;                 // :65
+	f->step_dist = 5.0 * 0.05;            // :68
+	f->ortho_width = 2.0 * 0.05;          // :98
+	f->cycle = 0;
+	f->cycle_period = 1;                  // the reference's default is 47 (:71); 1 renders a whole frame
+	f->traversal = HMRM_TRAVERSAL_AUTO;
+}
+
+int hmrm_render_device(hmrm_ctx *c, const hmrm_frame *f, void *d_rgba_out, void *stream) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!d_rgba_out) return fail(c, HMRM_ERR_INVALID, "d_rgba_out is NULL");
+	return enqueue_render(c, f, (uint32_t *)d_rgba_out, stream ? (cudaStream_t)stream : c->stream, true);
+}
+
+int hmrm_render_async(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!f) return fail(c, HMRM_ERR_INVALID, "frame is NULL");
+	if (!rgba_out) return fail(c, HMRM_ERR_INVALID, "rgba_out is NULL");
+	if (f->screen_width < 2 || f->screen_height < 2 || f->screen_width > 65536 || f->screen_height > 65536)
+		return fail(c, HMRM_ERR_INVALID, "resolution %dx%d outside [2,65536]", f->screen_width, f->screen_height);
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	int rc = ensure_framebuffer(c, f->screen_width, f->screen_height);
+	if (rc) return rc;
+	rc = enqueue_render(c, f, c->d_fb, c->stream, true);
+	if (rc) return rc;
+	int rb = f->row_begin, re = f->row_end;
+	if (rb == 0 && re == 0) re = f->screen_height;
+	const size_t row_bytes = (size_t)f->screen_width * 4;
+	HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + (size_t)rb * row_bytes, (const uint8_t *)c->d_fb + (size_t)rb * row_bytes,
+	                             (size_t)(re - rb) * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+	return HMRM_OK;
+}
+
+int hmrm_wait(hmrm_ctx *c) {
+	if (!c) return HMRM_ERR_INVALID;
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	return HMRM_OK;
+}
+
+int hmrm_render(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
+	int rc = hmrm_render_async(c, f, rgba_out);
+	if (rc) return rc;
+	return hmrm_wait(c);
+}
+
+int hmrm_get_stats(hmrm_ctx *c, hmrm_stats *out) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!out) return fail(c, HMRM_ERR_INVALID, "out is NULL");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	std::memset(out, 0, sizeof *out);
+	DeviceStats ds;
+	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats, sizeof ds, cudaMemcpyDeviceToHost));
+	if (c->last_had_stats) {
+		out->rays = (int64_t)ds.rays;
+		out->box_hits = (int64_t)ds.box_hits;
+		out->surf_hits = (int64_t)ds.surf_hits;
+		out->steps = (int64_t)ds.steps;
+		out->fetches = (int64_t)ds.fetches;
+		out->max_steps = (int64_t)ds.max_steps;
+	}
+	out->status = (int32_t)ds.status;
+	if (c->timing_valid) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) out->kernel_ms = ms;
+	}
+	return HMRM_OK;
+}
+
+int hmrm_get_step_index(hmrm_ctx *c, int32_t *step_index) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!step_index) return fail(c, HMRM_ERR_INVALID, "step_index is NULL");
+	if (!c->last_had_step_index) return fail(c, HMRM_ERR_STATE, "last render did not set HMRM_FLAG_STEP_INDEX");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	HMRM_CUDA(c, cudaMemcpy(step_index, c->d_step_index, (size_t)c->last_w * (size_t)c->last_h * 4,
+	                        cudaMemcpyDeviceToHost));
+	return HMRM_OK;
+}
+
+double hmrm_deg2rad(double degrees) { return deg2rad(degrees); }
+
+void hmrm_camera_basis(double hang, double vang, double look[3], double up[3]) {
+	Vec3 l, u;
+	camera_basis(hang, vang, &l, &u);
+	look[0] = l.x; look[1] = l.y; look[2] = l.z;
+	up[0] = u.x; up[1] = u.y; up[2] = u.z;
+}
+
+int hmrm_get_ray(const hmrm_frame *f, double w, double h, double pos[3], double dir[3]) {
+	if (!f || !pos || !dir) return HMRM_ERR_INVALID;
+	if (f->projection < HMRM_PERSPECTIVE || f->projection > HMRM_ORTHOGRAPHIC) return HMRM_ERR_INVALID;
+	const PlaneConst pc = build_plane(*f);
+	Vec3 p, d;
+	plane_ray(pc, w, h, &p, &d);
+	pos[0] = p.x; pos[1] = p.y; pos[2] = p.z;
+	dir[0] = d.x; dir[1] = d.y; dir[2] = d.z;
+	return HMRM_OK;
+}
+
+int hmrm_host_alloc(void **ptr, size_t bytes) {
+	if (!ptr) return HMRM_ERR_INVALID;
+	*ptr = NULL;
+	cudaError_t e = cudaMallocHost(ptr, bytes);
+	if (e != cudaSuccess) return fail(NULL, HMRM_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+	return HMRM_OK;
+}
+
+void hmrm_host_free(void *ptr) {
+	if (ptr) cudaFreeHost(ptr);
+}
+
+} // extern "C"

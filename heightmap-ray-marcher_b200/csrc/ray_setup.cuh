@@ -1,0 +1,116 @@
+// Per-pixel front end shared by the render kernels: ray generation for the three
+// projections, AABB slab entry, miss shading, pixel store.
+//
+// Arithmetic contract (operation order = rounding order), reference lines:
+//   Perspective::GetRay   src/Perspective.cpp:25-32
+//   Spherical::GetRay     src/Spherical.cpp:17-31 (trig factors come from host tables)
+//   Orthographic::GetRay  src/Orthographic.cpp:19-25
+//   distance/intersection src/AABB.cpp:30-77
+//   miss shading          main/hmap.cpp:1041-1057
+//   SetPixel              main/hmap.cpp:139-154
+#ifndef HMRM_RAY_SETUP_CUH
+#define HMRM_RAY_SETUP_CUH
+
+#include "device_math.cuh"
+#include "render_params.h"
+
+namespace hmrm {
+
+struct Ray {
+	double ox, oy, oz;
+	double dx, dy, dz;
+};
+
+__device__ __forceinline__ Ray generate_ray(const RenderParams &P, int px, int py) {
+	Ray r;
+	if (P.projection == 2) {
+		const double sv = __ldg(P.sin_va + py);
+		r.ox = P.cam[0]; r.oy = P.cam[1]; r.oz = P.cam[2];
+		r.dx = fmul(sv, __ldg(P.cos_ha + px));
+		r.dy = fmul(sv, __ldg(P.sin_ha + px));
+		r.dz = __ldg(P.cos_va + py);
+		return r;
+	}
+	const double w = __ldg(P.wtab + px);
+	const double h = __ldg(P.htab + py);
+	// (upper_left + w * plane_right) + h * plane_down
+	const double qx = fadd(fadd(P.ul[0], fmul(w, P.pr[0])), fmul(h, P.pd[0]));
+	const double qy = fadd(fadd(P.ul[1], fmul(w, P.pr[1])), fmul(h, P.pd[1]));
+	const double qz = fadd(fadd(P.ul[2], fmul(w, P.pr[2])), fmul(h, P.pd[2]));
+	if (P.projection == 1) {
+		const double vx = fsub(qx, P.cam[0]);
+		const double vy = fsub(qy, P.cam[1]);
+		const double vz = fsub(qz, P.cam[2]);
+		// glm::normalize: v * (1 / sqrt(dot(v, v))), dot = (x*x + y*y) + z*z
+		const double len2 = fadd(fadd(fmul(vx, vx), fmul(vy, vy)), fmul(vz, vz));
+		const double inv = fdiv(1.0, fsqrt(len2));
+		r.ox = P.cam[0]; r.oy = P.cam[1]; r.oz = P.cam[2];
+		r.dx = fmul(vx, inv);
+		r.dy = fmul(vy, inv);
+		r.dz = fmul(vz, inv);
+	}
+	else {
+		r.ox = qx; r.oy = qy; r.oz = qz;
+		r.dx = P.look[0]; r.dy = P.look[1]; r.dz = P.look[2];
+	}
+	return r;
+}
+
+// One axis of the slab test; returns false when the ray misses (src/AABB.cpp:58-73).
+__device__ __forceinline__ bool slab_axis(double c0, double c1, double o, double d, double &lo, double &hi) {
+	double t_near = fdiv(fsub(c0, o), d);
+	double t_far = fdiv(fsub(c1, o), d);
+	if (t_near > t_far) {
+		const double t = t_near;
+		t_near = t_far;
+		t_far = t;
+	}
+	if (t_far < lo || t_near > hi) return false;
+	if (t_near > lo) lo = t_near;
+	if (t_far < hi) hi = t_far;
+	return true;
+}
+
+// intersection(): true and the entry point when the ray enters the box at a distance d with 0 <= d < inf.
+__device__ __forceinline__ bool box_entry(const RenderParams &P, const Ray &r, double &ex, double &ey, double &ez) {
+	double lo = -__longlong_as_double(0x7FF0000000000000LL);
+	double hi = __longlong_as_double(0x7FF0000000000000LL);
+	if (!slab_axis(P.c0[0], P.c1[0], r.ox, r.dx, lo, hi)) return false;
+	if (!slab_axis(P.c0[1], P.c1[1], r.oy, r.dy, lo, hi)) return false;
+	if (!slab_axis(P.c0[2], P.c1[2], r.oz, r.dz, lo, hi)) return false;
+	if (lo > hi) return false;
+	// d == +inf cannot be reached here with lo <= hi unless hi is inf too; keep the reference's tests
+	if (lo == __longlong_as_double(0x7FF0000000000000LL)) return false;
+	if (lo < 0.0) return false;
+	ex = fadd(r.ox, fmul(lo, r.dx));
+	ey = fadd(r.oy, fmul(lo, r.dy));
+	ez = fadd(r.oz, fmul(lo, r.dz));
+	return true;
+}
+
+__device__ __forceinline__ uint32_t sky_channel(double v) {
+	if (v < 0.0) v = 0.0;
+	else if (v > 255.0) v = 255.0;
+	return (uint32_t)__double2uint_rd(v);   // (Uint8)floor(v), v in [0,255]
+}
+
+// colour of a ray that hit nothing (main/hmap.cpp:1041-1057); alpha 255
+__device__ __forceinline__ uint32_t miss_colour(const RenderParams &P, double dz) {
+	if (dz > 0.0) {
+		const double zz = fmul(dz, dz);   // std::pow(z, 2) == z*z under -std=c++98
+		const uint32_t r = sky_channel(fadd(fmul(220.0, zz), (double)P.bg[0]));
+		const uint32_t g = sky_channel(fadd(fmul(240.0, zz), (double)P.bg[1]));
+		const uint32_t b = sky_channel(fadd(fmul(255.0, dz), (double)P.bg[2]));
+		return r | (g << 8) | (b << 16) | 0xFF000000u;
+	}
+	return P.bg_rgba;
+}
+
+// colour of a terrain hit (main/hmap.cpp:1018-1031): alpha-0 texels draw the background colour
+__device__ __forceinline__ uint32_t hit_colour(const RenderParams &P, uint32_t texel) {
+	return ((texel >> 24) == 0u) ? P.bg_rgba : (texel | 0xFF000000u);
+}
+
+} // namespace hmrm
+
+#endif

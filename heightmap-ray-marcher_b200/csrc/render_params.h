@@ -1,0 +1,56 @@
+// Kernel-side view of one frame: everything K2 needs, passed by value as a
+// __grid_constant__ parameter (no constant-memory upload, no per-frame malloc).
+#ifndef HMRM_RENDER_PARAMS_H
+#define HMRM_RENDER_PARAMS_H
+
+#include <stdint.h>
+
+namespace hmrm {
+
+struct DeviceStats {
+	unsigned long long rays;
+	unsigned long long box_hits;
+	unsigned long long surf_hits;
+	unsigned long long steps;      // reference-equivalent march steps
+	unsigned long long fetches;    // loads actually issued on the march
+	unsigned long long max_steps;
+	unsigned int status;           // HMRM_ERR_NONTERMINATING if a ray was cut off
+	unsigned int pad;
+};
+
+struct RenderParams {
+	// screen
+	int projection;
+	int W, H;
+	int row_begin, row_end;
+	int cycle, period;
+	int tiles_x, tiles_y;          // 8x4-pixel tiles covering rows [row_begin,row_end)
+	// map
+	int map_w, map_h;
+	// image plane (host-built, frame_setup.h)
+	double cam[3], ul[3], pr[3], pd[3], look[3];
+	// AABB (main/hmap.cpp:967-974) and march constants
+	double c0[3], c1[3];
+	double gw;                     // grid_width
+	double nudge;                  // fl(grid_width * 0.01), :998
+	double step_dist;
+	double max_surf;               // max over cells of fl(height + min_height)
+	// tables (device pointers)
+	const double *wtab, *htab;     // px/(W-1), py/(H-1)
+	const double *cos_ha, *sin_ha, *sin_va, *cos_va;   // spherical only
+	// map planes
+	const double *surf;            // fl(height + min_height), row-major [map_h][map_w]
+	const uint32_t *color;         // RGBA8 little-endian, row-major
+	// outputs
+	uint32_t *fb;                  // RGBA8 [H][W]
+	int32_t *step_index;           // optional [H][W]
+	DeviceStats *stats;            // optional
+	unsigned int *tile_counter;    // persistent-thread tile queue head
+	uint32_t bg_rgba;              // bg colour with alpha 255
+	uint8_t bg[3];
+	uint8_t pad;
+};
+
+} // namespace hmrm
+
+#endif

@@ -1,0 +1,143 @@
+/* hmrm.h — C ABI of the B200-native heightmap ray-march path (libhmrm.so).
+ *
+ * The reference (Costava/heightmap-ray-marcher) has no library or FFI seam: its
+ * hot path is inline in main() and parameterised by global variables
+ * (main/hmap.cpp:28-112).  This header is the seam a maintainer would bind
+ * instead: each entry point names the reference lines it replaces.  All
+ * arguments are plain pointers, sizes and PODs; no C++ or torch types cross it.
+ *
+ * Conventions: every function returns 0 on success or an HMRM_ERR_* code;
+ * hmrm_last_error() gives the message.  The caller owns every host buffer it
+ * passes; the context owns all device memory.  A context is bound to one CUDA
+ * device and must be used from one host thread at a time.  Nothing in this
+ * library falls back to the CPU: without a CUDA device hmrm_create() fails.
+ */
+#ifndef HMRM_H
+#define HMRM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMRM_ABI_VERSION 1
+
+/* image_plane values, main/hmap.cpp:104-107 */
+#define HMRM_PERSPECTIVE  1
+#define HMRM_SPHERICAL    2
+#define HMRM_ORTHOGRAPHIC 3
+
+/* arithmetic mode of the render kernel */
+#define HMRM_FP64_EXACT 0   /* bit-exact to the reference's RGBA8 framebuffer */
+#define HMRM_FP32_FAST  1   /* FP32 march, >= 99.5 % identical pixels */
+
+/* traversal strategy (results are identical; this selects the kernel) */
+#define HMRM_TRAVERSAL_AUTO  0
+#define HMRM_TRAVERSAL_BRUTE 1   /* one height fetch per reference step (main/hmap.cpp:1000-1038 as written) */
+#define HMRM_TRAVERSAL_SKIP  2   /* conservative max-mip empty-space skip in whole steps */
+
+/* hmrm_frame.flags */
+#define HMRM_FLAG_STATS      1u  /* count rays / steps / fetches (hmrm_get_stats) */
+#define HMRM_FLAG_STEP_INDEX 2u  /* record the per-pixel first-hit step index (hmrm_get_step_index) */
+
+#define HMRM_OK                  0
+#define HMRM_ERR_INVALID         1   /* bad argument */
+#define HMRM_ERR_CUDA            2   /* CUDA runtime error (message has the detail) */
+#define HMRM_ERR_STATE           3   /* call order: maps / heightmap not set */
+#define HMRM_ERR_NONTERMINATING  4   /* a ray can never leave the grid: the reference would hang (main/hmap.cpp:1000) */
+
+typedef struct hmrm_ctx hmrm_ctx;
+
+/* The reference's per-frame render state (globals, main/hmap.cpp:28-112), as one POD.
+ * Angles are radians, as the reference stores them after DegreesToRads (:131-133). */
+typedef struct hmrm_frame {
+	int32_t projection;     /* image_plane :107 */
+	int32_t screen_width;   /* :31 */
+	int32_t screen_height;  /* :32 */
+	int32_t precision;      /* HMRM_FP64_EXACT | HMRM_FP32_FAST */
+	double cam_pos[3];      /* :75 */
+	double hang;            /* :80 */
+	double vang;            /* :85 */
+	double hfov;            /* :35 */
+	double ortho_width;     /* :98 */
+	double grid_width;      /* :65 */
+	double step_dist;       /* :68 */
+	uint8_t bg[3];          /* bg_r, bg_g, bg_b :110-112 */
+	uint8_t reserved0;
+	int32_t cycle;          /* first pixel index of this frame (:979), 0 <= cycle < cycle_period */
+	int32_t cycle_period;   /* pixel stride (:71,:980); 1 = full frame */
+	int32_t row_begin;      /* rows [row_begin,row_end) are rendered: row band of a multi-GPU frame */
+	int32_t row_end;        /* 0,0 = all rows */
+	int32_t traversal;      /* HMRM_TRAVERSAL_* */
+	uint32_t flags;         /* HMRM_FLAG_* */
+} hmrm_frame;
+
+typedef struct hmrm_stats {
+	int64_t rays;           /* pixels rendered */
+	int64_t box_hits;       /* rays that entered the AABB (src/AABB.cpp:30) */
+	int64_t surf_hits;      /* rays that hit the terrain (main/hmap.cpp:1016) */
+	int64_t steps;          /* reference-equivalent march steps = height fetches the reference performs (:1013) */
+	int64_t fetches;        /* memory fetches this kernel actually issued on the march (any level) */
+	int64_t max_steps;      /* longest single ray, in reference steps */
+	int32_t status;         /* 0, or HMRM_ERR_NONTERMINATING if some ray was cut off */
+	int32_t reserved0;
+	double kernel_ms;       /* CUDA-event duration of the render kernel */
+} hmrm_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int hmrm_abi_version(void);
+int hmrm_device_count(void);
+int hmrm_create(int device, hmrm_ctx **out);
+void hmrm_destroy(hmrm_ctx *ctx);
+const char *hmrm_last_error(const hmrm_ctx *ctx);   /* ctx may be NULL: last creation error */
+
+/* ---- maps: replaces stbi_load results at main/hmap.cpp:320-321 (RGB8) and :341-342 (RGBA8) ---- */
+int hmrm_set_maps(hmrm_ctx *ctx, const uint8_t *height_rgb8, const uint8_t *color_rgba8,
+                  int32_t map_width, int32_t map_height);
+/* same, from device memory of ctx's device (copied) */
+int hmrm_set_maps_device(hmrm_ctx *ctx, const void *d_height_rgb8, const void *d_color_rgba8,
+                         int32_t map_width, int32_t map_height);
+/* synthetic fBm maps of size 2^log2n generated on the device (csrc/synth_fbm.h; bench / test input) */
+int hmrm_synth_maps(hmrm_ctx *ctx, uint32_t log2n, uint32_t seed);
+int hmrm_get_maps(hmrm_ctx *ctx, uint8_t *height_rgb8, uint8_t *color_rgba8);   /* download (either may be NULL) */
+
+/* ---- prepass: replaces UpdateHeightmap, main/hmap.cpp:171-191 (kernel K1) ---- */
+int hmrm_update_heightmap(hmrm_ctx *ctx, const double lum[3], double min_height, double max_height);
+/* heights exactly as the reference's heightmap_buf (double[H][W], main/hmap.cpp:53), for parity checks */
+int hmrm_get_heights(hmrm_ctx *ctx, double *heights);
+
+/* ---- render: replaces main/hmap.cpp:952-1058 (ImagePlane ctor + pixel loop; kernel K2) ---- */
+void hmrm_frame_defaults(hmrm_frame *f);            /* the reference's defaults, :31-112, cycle_period 1 */
+/* rgba_out: host RGBA8 [screen_height][screen_width][4], stride W*4 — the reference's framebuf (:612).
+ * Only the pixels selected by cycle/cycle_period and the row band are written. Synchronous. */
+int hmrm_render(hmrm_ctx *ctx, const hmrm_frame *f, uint8_t *rgba_out);
+/* device output (same layout) on `stream` (a cudaStream_t, NULL = ctx's own stream); asynchronous */
+int hmrm_render_device(hmrm_ctx *ctx, const hmrm_frame *f, void *d_rgba_out, void *stream);
+/* persistent device framebuffer: render into it, copy rows [row_begin,row_end) to (pinned) host memory
+ * asynchronously; hmrm_wait() joins.  Used for frame sharding (one frame in flight per context). */
+int hmrm_render_async(hmrm_ctx *ctx, const hmrm_frame *f, uint8_t *rgba_out);
+int hmrm_wait(hmrm_ctx *ctx);
+
+int hmrm_get_stats(hmrm_ctx *ctx, hmrm_stats *out);            /* of the last render */
+int hmrm_get_step_index(hmrm_ctx *ctx, int32_t *step_index);   /* int32 [H][W]: first-hit sample index,
+                                                                  -1 box missed, -2 no surface hit */
+
+/* ---- type-level API mirror (host side; no device work) ---- */
+/* DegreesToRads, main/hmap.cpp:131-133 */
+double hmrm_deg2rad(double degrees);
+/* look/up from hang,vang, main/hmap.cpp:661-672 */
+void hmrm_camera_basis(double hang, double vang, double look[3], double up[3]);
+/* ImagePlane::GetRay (src/ImagePlane.hpp:10) of the plane the frame describes; w,h in [0,1] */
+int hmrm_get_ray(const hmrm_frame *f, double w, double h, double pos[3], double dir[3]);
+
+/* pinned host memory helpers (so that callers without a CUDA binding can stage buffers) */
+int hmrm_host_alloc(void **ptr, size_t bytes);
+void hmrm_host_free(void *ptr);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif

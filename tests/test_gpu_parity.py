@@ -1,0 +1,198 @@
+"""GPU: the CUDA path, called through the C ABI (libhmrm.so), against the CPU oracle on the same seeded
+inputs and against the committed fixtures produced by the unmodified reference.
+
+Bar: bit-exact RGBA8 framebuffer, identical per-pixel first-hit step index, identical step statistics
+(FP64 exact mode).  Full-size cases are checked through size-independent properties.
+"""
+import numpy as np
+import pytest
+
+import helpers as H
+import scenes as S
+
+pytestmark = pytest.mark.gpu
+
+TRAVERSALS = [1, 2]   # HMRM_TRAVERSAL_BRUTE, HMRM_TRAVERSAL_SKIP
+
+
+@pytest.mark.parametrize("traversal", TRAVERSALS)
+@pytest.mark.parametrize("scene", S.SCENES, ids=lambda s: s["name"])
+def test_frame_bit_exact_vs_reference_golden_and_oracle(hmrm, renderer, oracle, scene, traversal):
+    maps = H.load_scene_maps(scene, oracle)
+    H.configure(renderer, scene, maps)
+    f = H.product_frame(hmrm, renderer, scene, traversal=traversal,
+                        flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX)
+    got = renderer.render(f)
+    st = renderer.stats()
+    steps = renderer.step_index(f)
+
+    meta = H.golden_meta()[scene["name"]]
+    want = H.golden_frames()[scene["name"]]
+    diff = int((got != want).any(axis=2).sum())
+    assert diff == 0, f"{diff} pixels differ from the reference's frame"
+    assert H.sha(got) == meta["sha256"]
+
+    ofb, osteps, ost = H.oracle_render_scene(oracle, scene, maps)
+    assert np.array_equal(got, ofb)
+    assert np.array_equal(steps, osteps), f"{int((steps != osteps).sum())} first-hit step indices differ"
+    assert (st.rays, st.box_hits, st.surf_hits, st.steps, st.max_steps) == (
+        ost.rays, ost.box_hits, ost.surf_hits, ost.steps, ost.max_steps)
+    assert st.status == 0
+    if traversal == 1:
+        assert st.fetches == st.steps
+    else:
+        assert st.fetches <= st.steps + st.box_hits * 64
+
+
+@pytest.mark.parametrize("name", ["noise_lum", "noise_lum_neg", "min_height_twice", "defaults_grid"])
+def test_prepass_heights_bit_exact(hmrm, renderer, oracle, name):
+    scene = S.SCENE_BY_NAME[name]
+    hm, cm = H.load_scene_maps(scene, oracle)
+    H.configure(renderer, scene, (hm, cm))
+    got = renderer.heights()
+    want = oracle.update_heightmap(hm, scene["lum"], scene["min_height"], scene["max_height"])
+    assert got.tobytes() == want.tobytes()
+    assert H.sha(got) == H.golden_meta()[name]["heights_sha256"]
+
+
+def test_prepass_heights_kat(hmrm, renderer):
+    """UpdateHeightmap known answers from the unmodified reference (tests/golden/kat.json)."""
+    for rec in H.golden_kat()["heights"]:
+        rgb = np.random.RandomState(rec["rgb_seed"]).randint(0, 256, size=(64, 64, 3)).astype(np.uint8)
+        rgb[0, :8] = [[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [1, 1, 1],
+                      [254, 255, 253], [128, 128, 128]]
+        renderer.lum_r, renderer.lum_g, renderer.lum_b = [H.fx(v) for v in rec["lum"]]
+        renderer.min_height, renderer.max_height = H.fx(rec["min_height"]), H.fx(rec["max_height"])
+        renderer.set_maps(rgb, np.zeros((64, 64, 4), dtype=np.uint8))
+        assert H.sha(renderer.heights()) == rec["sha256"]
+
+
+def test_synth_maps_device_equals_cpu_generator(hmrm, renderer, oracle):
+    for log2n in (6, 9):
+        renderer.synth_maps(log2n, 1234)
+        hm, cm = renderer.get_maps()
+        ohm, ocm = oracle.synth_maps(log2n, 1234)
+        assert np.array_equal(hm, ohm) and np.array_equal(cm, ocm)
+
+
+@pytest.mark.parametrize("traversal", TRAVERSALS)
+def test_cycle_interleave_accumulates_to_full_frame(hmrm, renderer, oracle, traversal):
+    """cycle / cycle_period (main/hmap.cpp:976-981): the persistent framebuffer is not cleared between
+    frames, so cycle_period frames with successive phases add up to the full image."""
+    scene = S.SCENE_BY_NAME["spher_basic"]
+    maps = H.load_scene_maps(scene, oracle)
+    H.configure(renderer, scene, maps)
+    full = renderer.render(H.product_frame(hmrm, renderer, scene, traversal=traversal)).copy()
+    # different resolution forces a fresh (zeroed) framebuffer, then back
+    renderer.render(H.product_frame(hmrm, renderer, scene, traversal=traversal, screen_width=64, screen_height=32))
+    period = 47   # the reference's default (main/hmap.cpp:71)
+    out = None
+    for phase in range(period):
+        out = renderer.render(H.product_frame(hmrm, renderer, scene, traversal=traversal, cycle=phase,
+                                              cycle_period=period))
+        if phase == 0:
+            first = out.copy()
+    assert np.array_equal(out, full)
+    sel = np.zeros(full.shape[:2], dtype=bool).reshape(-1)
+    sel[0::period] = True
+    sel = sel.reshape(full.shape[:2])
+    assert np.array_equal(first[sel], full[sel]) and not first[~sel].any()
+
+
+@pytest.mark.parametrize("traversal", TRAVERSALS)
+def test_row_bands_concatenate_to_full_frame(hmrm, renderer, oracle, traversal):
+    """Row-band partition used for multi-GPU frames: bands rendered separately == one full frame."""
+    scene = S.SCENE_BY_NAME["persp_graze"]
+    maps = H.load_scene_maps(scene, oracle)
+    H.configure(renderer, scene, maps)
+    full = renderer.render(H.product_frame(hmrm, renderer, scene, traversal=traversal)).copy()
+    Hh = scene["height"]
+    out = np.zeros_like(full)
+    edges = [0, 57, 58, 113, 200, Hh]
+    for a, b in zip(edges[:-1], edges[1:]):
+        band = np.zeros_like(full)
+        renderer.render(H.product_frame(hmrm, renderer, scene, traversal=traversal, row_begin=a, row_end=b), out=band)
+        out[a:b] = band[a:b]
+    assert np.array_equal(out, full)
+
+
+def test_render_device_and_async_paths_agree(hmrm, renderer, oracle):
+    import torch
+
+    scene = S.SCENE_BY_NAME["ortho_basic"]
+    maps = H.load_scene_maps(scene, oracle)
+    H.configure(renderer, scene, maps)
+    f = H.product_frame(hmrm, renderer, scene)
+    want = renderer.render(f).copy()
+    dev = torch.zeros((scene["height"], scene["width"], 4), dtype=torch.uint8, device="cuda:0")
+    renderer.render_device(f, dev)
+    renderer.wait()
+    assert np.array_equal(dev.cpu().numpy(), want)
+    from heightmap_ray_marcher_b200 import binding
+
+    pinned = binding.pinned_empty(want.shape)
+    pinned[:] = 0
+    renderer.render_async(f, pinned)
+    renderer.wait()
+    assert np.array_equal(pinned, want)
+
+
+def test_invalid_arguments_are_rejected(hmrm, renderer, oracle):
+    scene = S.SCENE_BY_NAME["persp_basic"]
+    H.configure(renderer, scene, H.load_scene_maps(scene, oracle))
+    for bad in (dict(step_dist=0.0), dict(step_dist=-1.0), dict(grid_width=0.0), dict(cycle_period=0),
+                dict(projection=4), dict(screen_width=1), dict(row_begin=10, row_end=5),
+                dict(step_dist=float("nan"))):
+        with pytest.raises(hmrm.HmrmError):
+            renderer.render(H.product_frame(hmrm, renderer, scene, **bad))
+
+
+def test_nonterminating_ray_is_cut_off_and_flagged(hmrm, renderer, oracle):
+    """straight-up orthographic rays under a flat zero terrain never leave the grid in
+    the reference (it hangs); the kernel must terminate and flag the frame."""
+    hm = np.zeros((32, 32, 3), dtype=np.uint8)
+    cm = np.full((32, 32, 4), 255, dtype=np.uint8)
+    renderer.lum_r, renderer.lum_g, renderer.lum_b = 0.0, 0.0, 0.0
+    renderer.min_height, renderer.max_height = 0.0, 10.0
+    renderer.set_maps(hm, cm)
+    for traversal in TRAVERSALS:
+        f = renderer.frame(projection=3, screen_width=16, screen_height=8, cam_pos=(0.8, -0.8, -3.0),
+                           hang=0.0, vang=0.0, ortho_width=0.01, grid_width=0.05, step_dist=0.25,
+                           traversal=traversal, flags=hmrm.FLAG_STATS)
+        out = renderer.render(f)
+        st = renderer.stats()
+        assert st.status == 4   # HMRM_ERR_NONTERMINATING
+        assert (out[..., 3] == 255).all()
+
+
+@pytest.mark.parametrize("log2n,proj,res", [(11, 1, (1920, 1080)), (12, 2, (1920, 1080))])
+def test_large_frame_properties(hmrm, renderer, oracle, log2n, proj, res):
+    """Sizes the oracle cannot cover quickly in full: BRUTE == SKIP (frame, step index, step totals),
+    a sampled row band == oracle, alpha is 255 everywhere."""
+    renderer.lum_r, renderer.lum_g, renderer.lum_b = S.DEFAULT_LUM
+    renderer.min_height, renderer.max_height = 0.0, 10.0
+    renderer.synth_maps(log2n, 1234)
+    n = 1 << log2n
+    W, Hh = res
+    common = dict(projection=proj, screen_width=W, screen_height=Hh, cam_pos=(-0.2 * n * 0.01, 0.2 * n * 0.01, 16.0),
+                  hang=hmrm.deg2rad(-45.0), vang=hmrm.deg2rad(115.0), hfov=hmrm.deg2rad(90.0), grid_width=0.01,
+                  step_dist=0.05, ortho_width=0.03, flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX)
+    fb = renderer.frame(traversal=1, **common)
+    a = renderer.render(fb).copy()
+    sa, ia = renderer.stats(), renderer.step_index(fb)
+    fs = renderer.frame(traversal=2, **common)
+    b = renderer.render(fs).copy()
+    sb, ib = renderer.stats(), renderer.step_index(fs)
+    assert np.array_equal(a, b) and np.array_equal(ia, ib)
+    assert (sa.rays, sa.box_hits, sa.surf_hits, sa.steps, sa.max_steps) == (sb.rays, sb.box_hits, sb.surf_hits,
+                                                                             sb.steps, sb.max_steps)
+    assert (a[..., 3] == 255).all() and sa.surf_hits > 0
+
+    hm, cm = renderer.get_maps()
+    heights = oracle.update_heightmap(hm, S.DEFAULT_LUM, 0.0, 10.0)
+    of = oracle.make_frame(projection=proj, width=W, height=Hh, pos=common["cam_pos"], hang_deg=-45.0,
+                           vang_deg=115.0, hfov_deg=90.0, grid_width=0.01, step_dist=0.05, ortho_width=0.03)
+    rows = (Hh // 2 - 12, Hh // 2 + 12)
+    ofb, osteps, _ = oracle.render(of, heights, cm, rows=rows)
+    assert np.array_equal(a[rows[0]:rows[1]], ofb[rows[0]:rows[1]])
+    assert np.array_equal(ia[rows[0]:rows[1]], osteps[rows[0]:rows[1]])
