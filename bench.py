@@ -244,7 +244,8 @@ def ours_arm(args, wl) -> None:
     warm_frames = [((args.steps + s) * world + rank) % wl["frames"] for s in range(args.warmup)]
     d_out = torch.empty((H, W, 4), dtype=torch.uint8, device=f"cuda:{local}")
     h_out = binding.pinned_empty((H, W, 4))
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=local)       # a real (non-default) stream: kernels and events share it
+    torch.cuda.set_stream(stream)
 
     # ---- untimed statistics pass over the timed frames: reference-equivalent steps S, hits, fetches ----
     S = hits = fetches = 0

@@ -18,6 +18,7 @@
 #include "frame_setup.h"
 #include "k1_prepass.cuh"
 #include "k2_render_brute.cuh"
+#include "k2_render_skip.cuh"
 #include "render_params.h"
 #include "synth_fbm.h"
 
@@ -48,9 +49,16 @@ struct hmrm_ctx {
 	uint8_t *d_rgb;              // RGB8 [map_h][map_w][3]
 	uint32_t *d_color;           // RGBA8
 	double *d_surf;              // fl(height + min_height)
-	unsigned long long *d_max_bits;
+	unsigned long long *d_max_bits;  // [0] max, [1] min of surf (order-preserving bits); [2] quantiser error flag
 	bool maps_set, heights_set;
-	double lum[3], min_height, max_height, max_surf;
+	double lum[3], min_height, max_height, max_surf, min_surf;
+	// conservative fixed-point view for the skip traversal
+	uint16_t *d_mip;             // levels 0..mip_levels-1 back to back; level 0 = Zq(surf) per cell
+	size_t mip_offset[16];
+	int mip_w[16], mip_h[16];
+	int mip_levels;
+	double zq_scale, zq_offset;
+	bool skip_ready;
 
 	// per-resolution tables
 	int tab_w, tab_h;
@@ -112,6 +120,8 @@ void free_maps(hmrm_ctx *c) {
 	cudaFree(c->d_rgb);
 	cudaFree(c->d_color);
 	cudaFree(c->d_surf);
+	cudaFree(c->d_mip);
+	c->d_mip = NULL;
 	c->d_rgb = NULL;
 	c->d_color = NULL;
 	c->d_surf = NULL;
@@ -119,7 +129,8 @@ void free_maps(hmrm_ctx *c) {
 }
 
 int alloc_maps(hmrm_ctx *c, int32_t w, int32_t h) {
-	if (w < 1 || h < 1) return fail(c, HMRM_ERR_INVALID, "map size %dx%d is not positive", w, h);
+	if (w < 1 || h < 1 || w > 32768 || h > 32768)
+		return fail(c, HMRM_ERR_INVALID, "map size %dx%d outside [1,32768]", w, h);
 	HMRM_CUDA(c, cudaSetDevice(c->device));
 	if (c->maps_set && c->map_w == w && c->map_h == h) {
 		c->heights_set = false;
@@ -130,6 +141,21 @@ int alloc_maps(hmrm_ctx *c, int32_t w, int32_t h) {
 	HMRM_CUDA(c, cudaMalloc(&c->d_rgb, n * 3));
 	HMRM_CUDA(c, cudaMalloc(&c->d_color, n * 4));
 	HMRM_CUDA(c, cudaMalloc(&c->d_surf, n * 8));
+	// mip pyramid of 16-bit conservative heights: level l is ceil(w/2^l) x ceil(h/2^l), up to a single texel
+	size_t total = 0;
+	int lw = w, lh = h, levels = 0;
+	for (;;) {
+		c->mip_w[levels] = lw;
+		c->mip_h[levels] = lh;
+		c->mip_offset[levels] = total;
+		total += ((size_t)lw * (size_t)lh + 63) & ~(size_t)63;
+		levels += 1;
+		if ((lw == 1 && lh == 1) || levels == 16) break;
+		lw = (lw + 1) / 2;
+		lh = (lh + 1) / 2;
+	}
+	c->mip_levels = levels;
+	HMRM_CUDA(c, cudaMalloc(&c->d_mip, total * 2));
 	c->map_w = w;
 	c->map_h = h;
 	return HMRM_OK;
@@ -301,16 +327,50 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	HMRM_CUDA(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int), stream));
 	HMRM_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), stream));
 
+	int traversal = f->traversal;
+	if (traversal == HMRM_TRAVERSAL_AUTO) traversal = c->skip_ready ? HMRM_TRAVERSAL_SKIP : HMRM_TRAVERSAL_BRUTE;
+	if (traversal != HMRM_TRAVERSAL_BRUTE && traversal != HMRM_TRAVERSAL_SKIP)
+		return fail(c, HMRM_ERR_INVALID, "unknown traversal %d", f->traversal);
+	if (traversal == HMRM_TRAVERSAL_SKIP) {
+		if (!c->skip_ready)
+			return fail(c, HMRM_ERR_STATE, "the height range could not be quantised; use HMRM_TRAVERSAL_BRUTE");
+		int dim = c->map_w > c->map_h ? c->map_w : c->map_h, clog = 0;
+		while ((1 << clog) < dim) clog += 1;
+		P.fx_bits = 30 - clog < 20 ? 30 - clog : 20;
+		P.fx_scale = std::ldexp(1.0, P.fx_bits) / f->grid_width;
+		P.zq_scale = c->zq_scale;
+		P.zq_offset = c->zq_offset;
+		P.ltop = c->mip_levels - 1;
+		// lowest useful block: about two steps wide
+		const double step_cells = f->step_dist / f->grid_width;
+		int lmin = 1;
+		while (lmin < P.ltop && (double)(1 << lmin) < 2.0 * step_cells) lmin += 1;
+		P.lmin = lmin;
+		P.lstride = 2;
+		P.q0 = c->d_mip;
+		for (int l = 0; l < 16; ++l) {
+			P.mip[l] = (l < c->mip_levels) ? c->d_mip + c->mip_offset[l] : NULL;
+			P.mip_w[l] = (l < c->mip_levels) ? c->mip_w[l] : 0;
+		}
+		if (!std::isfinite(P.fx_scale)) traversal = HMRM_TRAVERSAL_BRUTE;
+	}
+
 	const int n_tiles = P.tiles_x * P.tiles_y;
 	const int warps_per_block = 8;
-	int blocks = c->num_sms * 8;   // 64 resident warps per SM at <= 32 registers... capped by occupancy anyway
+	int blocks = c->num_sms * 8;   // persistent CTAs; residency is whatever the register count allows
 	const int max_useful = (n_tiles + warps_per_block - 1) / warps_per_block;
 	if (blocks > max_useful) blocks = max_useful;
 	if (blocks < 1) blocks = 1;
 
 	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_begin, stream));
-	if (want_stats) k2_render_brute<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
-	else k2_render_brute<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+	if (traversal == HMRM_TRAVERSAL_SKIP) {
+		if (want_stats) k2_render_skip<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		else k2_render_skip<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+	}
+	else {
+		if (want_stats) k2_render_brute<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		else k2_render_brute<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+	}
 	HMRM_CUDA(c, cudaGetLastError());
 	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_end, stream));
 
@@ -367,7 +427,12 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->lum[2] = 0.114;
 	c->min_height = 0.0;
 	c->max_height = 10.0;
-	c->max_surf = 0.0;
+	c->max_surf = c->min_surf = 0.0;
+	c->d_mip = NULL;
+	c->mip_levels = 0;
+	c->zq_scale = 1.0;
+	c->zq_offset = HMRM_MAGIC;
+	c->skip_ready = false;
 	c->tab_w = c->tab_h = 0;
 	c->d_wtab = c->d_htab = c->d_sph = NULL;
 	c->sph_cap = 0;
@@ -394,7 +459,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 		err = cudaEventCreateWithFlags(&c->staging[i].consumed, cudaEventDisableTiming);
 	if (err == cudaSuccess) err = cudaMalloc(&c->d_stats, sizeof(DeviceStats));
 	if (err == cudaSuccess) err = cudaMalloc(&c->d_tile_counter, 256);
-	if (err == cudaSuccess) err = cudaMalloc(&c->d_max_bits, 8);
+	if (err == cudaSuccess) err = cudaMalloc(&c->d_max_bits, 32);
 	if (err != cudaSuccess) {
 		fail(NULL, HMRM_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));
 		hmrm_destroy(c);
@@ -490,13 +555,32 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 	q.min_height = min_height;
 	q.span = max_height - min_height;
 	const long long n = (long long)c->map_w * c->map_h;
-	HMRM_CUDA(c, cudaMemsetAsync(c->d_max_bits, 0, 8, c->stream));
-	k1_prepass<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, n, q, c->d_surf, NULL, c->d_max_bits);
+	const unsigned long long init_bits[3] = {0ULL, ~0ULL, 0ULL};
+	HMRM_CUDA(c, cudaMemcpyAsync(c->d_max_bits, init_bits, sizeof init_bits, cudaMemcpyHostToDevice, c->stream));
+	k1_prepass<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, n, q, c->d_surf, NULL, c->d_max_bits, c->d_max_bits + 1);
 	HMRM_CUDA(c, cudaGetLastError());
-	unsigned long long bits = 0;
-	HMRM_CUDA(c, cudaMemcpyAsync(&bits, c->d_max_bits, 8, cudaMemcpyDeviceToHost, c->stream));
+	unsigned long long bits[3] = {0ULL, 0ULL, 0ULL};
+	HMRM_CUDA(c, cudaMemcpyAsync(bits, c->d_max_bits, 16, cudaMemcpyDeviceToHost, c->stream));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
-	c->max_surf = from_ordered_bits(bits);
+	c->max_surf = from_ordered_bits(bits[0]);
+	c->min_surf = from_ordered_bits(bits[1]);
+
+	// Zq: surf range [min_surf, max_surf] -> [16, 65016] (16-bit, with headroom for the rounding of the constants)
+	const double range = c->max_surf - c->min_surf;
+	c->zq_scale = (range > 0.0 && std::isfinite(range) && std::isfinite(65000.0 / range)) ? 65000.0 / range : 1.0;
+	c->zq_offset = HMRM_MAGIC + (16.0 - c->min_surf * c->zq_scale);
+	k1_quantise<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_surf, n, c->zq_scale, c->zq_offset, c->d_mip,
+	                                                    (unsigned int *)(c->d_max_bits + 2));
+	HMRM_CUDA(c, cudaGetLastError());
+	for (int l = 1; l < c->mip_levels; ++l) {
+		k1_mip_reduce<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_mip + c->mip_offset[l - 1], c->mip_w[l - 1],
+		                                                      c->mip_h[l - 1], c->d_mip + c->mip_offset[l],
+		                                                      c->mip_w[l], c->mip_h[l]);
+		HMRM_CUDA(c, cudaGetLastError());
+	}
+	HMRM_CUDA(c, cudaMemcpyAsync(bits, c->d_max_bits + 2, 8, cudaMemcpyDeviceToHost, c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	c->skip_ready = (bits[0] == 0ULL) && std::isfinite(c->zq_offset);
 	c->lum[0] = lum[0];
 	c->lum[1] = lum[1];
 	c->lum[2] = lum[2];
@@ -520,7 +604,7 @@ int hmrm_get_heights(hmrm_ctx *c, double *heights) {
 	q.lum_b = c->lum[2];
 	q.min_height = c->min_height;
 	q.span = c->max_height - c->min_height;
-	k1_prepass<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, n, q, NULL, d_tmp, NULL);
+	k1_prepass<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, n, q, NULL, d_tmp, NULL, NULL);
 	cudaError_t e = cudaGetLastError();
 	if (e == cudaSuccess) e = cudaMemcpyAsync(heights, d_tmp, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

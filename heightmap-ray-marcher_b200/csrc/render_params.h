@@ -46,6 +46,14 @@ struct RenderParams {
 	int32_t *step_index;           // optional [H][W]
 	DeviceStats *stats;            // optional
 	unsigned int *tile_counter;    // persistent-thread tile queue head
+	// ---- skip traversal (k2_render_skip.cuh): fixed-point view of the march ----
+	double fx_scale;               // fl(2^fx_bits / grid_width): cell coordinate in 2^-fx_bits cell units
+	double zq_scale, zq_offset;    // Zq(z) = low32(fma(z, zq_scale, zq_offset)); same function quantises surf in K1
+	int fx_bits;                   // fractional bits of the fixed-point cell coordinate
+	int lmin, lstride, ltop;       // mip levels used this frame: lmin, lmin+lstride, ... <= ltop
+	const uint16_t *q0;            // Zq(surf) per cell, row-major [map_h][map_w]
+	const uint16_t *mip[16];       // mip[l]: max of q0 over 2^l x 2^l blocks, row-major, pitch mip_w[l]; mip[0] == q0
+	int mip_w[16];
 	uint32_t bg_rgba;              // bg colour with alpha 255
 	uint8_t bg[3];
 	uint8_t pad;
