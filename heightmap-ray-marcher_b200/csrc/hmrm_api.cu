@@ -77,6 +77,7 @@ struct hmrm_ctx {
 	unsigned int *d_tile_counter;
 	bool last_had_stats, last_had_step_index, timing_valid;
 	int last_w, last_h;
+	cudaStream_t last_stream;    // stream of the most recent render (the caller's, for hmrm_render_device)
 };
 
 namespace {
@@ -374,6 +375,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	HMRM_CUDA(c, cudaGetLastError());
 	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_end, stream));
 
+	c->last_stream = stream;
 	c->last_had_stats = want_stats;
 	c->last_had_step_index = want_steps;
 	c->timing_valid = timed;
@@ -416,6 +418,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->device = device;
 	c->num_sms = prop.multiProcessorCount;
 	c->stream = NULL;
+	c->last_stream = NULL;
 	c->map_w = c->map_h = 0;
 	c->d_rgb = NULL;
 	c->d_color = NULL;
@@ -451,6 +454,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->d_tile_counter = NULL;
 	c->last_had_stats = c->last_had_step_index = c->timing_valid = false;
 	c->last_w = c->last_h = 0;
+	c->last_stream = NULL;
 
 	cudaError_t err = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
 	if (err == cudaSuccess) err = cudaEventCreate(&c->ev_begin);
@@ -676,7 +680,7 @@ int hmrm_get_stats(hmrm_ctx *c, hmrm_stats *out) {
 	if (!c) return HMRM_ERR_INVALID;
 	if (!out) return fail(c, HMRM_ERR_INVALID, "out is NULL");
 	HMRM_CUDA(c, cudaSetDevice(c->device));
-	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
 	std::memset(out, 0, sizeof *out);
 	DeviceStats ds;
 	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats, sizeof ds, cudaMemcpyDeviceToHost));
@@ -701,7 +705,7 @@ int hmrm_get_step_index(hmrm_ctx *c, int32_t *step_index) {
 	if (!step_index) return fail(c, HMRM_ERR_INVALID, "step_index is NULL");
 	if (!c->last_had_step_index) return fail(c, HMRM_ERR_STATE, "last render did not set HMRM_FLAG_STEP_INDEX");
 	HMRM_CUDA(c, cudaSetDevice(c->device));
-	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
 	HMRM_CUDA(c, cudaMemcpy(step_index, c->d_step_index, (size_t)c->last_w * (size_t)c->last_h * 4,
 	                        cudaMemcpyDeviceToHost));
 	return HMRM_OK;

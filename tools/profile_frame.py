@@ -1,0 +1,38 @@
+"""Render a few frames of a bench workload and nothing else (short command line for ncu / compute-sanitizer)."""
+import argparse
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import bench  # noqa: E402
+import hmrm_pkg  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--workload", default="flythrough4k")
+ap.add_argument("--traversal", default="skip")
+ap.add_argument("--frames", type=int, default=4)
+ap.add_argument("--first", type=int, default=0)
+ap.add_argument("--stats", action="store_true")
+args = ap.parse_args()
+
+hmrm = hmrm_pkg.load()
+wl = bench.WORKLOADS[args.workload]
+r = hmrm.Renderer(0)
+r.min_height, r.max_height = bench.MIN_HEIGHT, bench.MAX_HEIGHT
+r.synth_maps(wl["log2n"], bench.SEED)
+trav = {"auto": 0, "brute": 1, "skip": 2}[args.traversal]
+for i in range(args.frames):
+    c = bench.camera(wl, args.first + i)
+    f = r.frame(projection=wl["projection"], screen_width=wl["W"], screen_height=wl["H"], cam_pos=c["pos"],
+                hang=hmrm.deg2rad(c["hang_deg"]), vang=hmrm.deg2rad(c["vang_deg"]), hfov=hmrm.deg2rad(c["hfov_deg"]),
+                ortho_width=c["ortho_width"], grid_width=bench.GRID_WIDTH, step_dist=wl["step_dist"], traversal=trav,
+                flags=hmrm.FLAG_STATS if args.stats else 0)
+    out = r.render(f)
+    st = r.stats()
+    print(f"frame {args.first + i}: kernel {st.kernel_ms:.3f} ms" +
+          (f" rays {st.rays} box {st.box_hits} surf {st.surf_hits} steps {st.steps} fetches {st.fetches} max {st.max_steps}"
+           if args.stats else ""))
+r.close()
