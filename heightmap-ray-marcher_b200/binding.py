@@ -89,6 +89,7 @@ PROTOTYPES = {
     "hmrm_wait": (C.c_int, [C.c_void_p]),
     "hmrm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "hmrm_get_step_index": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hmrm_get_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "hmrm_deg2rad": (C.c_double, [C.c_double]),
     "hmrm_camera_basis": (None, [C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "hmrm_get_ray": (C.c_int, [C.POINTER(Frame), C.c_double, C.c_double, C.POINTER(C.c_double),
@@ -290,6 +291,11 @@ class Renderer:
         st = Stats()
         self._check(self._lib.hmrm_get_stats(self._h, C.byref(st)))
         return st
+
+    def debug_counters(self) -> list:
+        out = (C.c_int64 * 8)()
+        self._check(self._lib.hmrm_get_debug_counters(self._h, out))
+        return list(out)
 
     def step_index(self, frame: Frame) -> np.ndarray:
         out = np.empty((frame.screen_height, frame.screen_width), dtype=np.int32)

@@ -348,6 +348,8 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		while (lmin < P.ltop && (double)(1 << lmin) < 2.0 * step_cells) lmin += 1;
 		P.lmin = lmin;
 		P.lstride = 2;
+		P.lstart = lmin + 2 * P.lstride <= P.ltop ? lmin + 2 * P.lstride : lmin;
+		if (P.fx_bits < 1) traversal = HMRM_TRAVERSAL_BRUTE;
 		P.q0 = c->d_mip;
 		for (int l = 0; l < 16; ++l) {
 			P.mip[l] = (l < c->mip_levels) ? c->d_mip + c->mip_offset[l] : NULL;
@@ -358,7 +360,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 
 	const int n_tiles = P.tiles_x * P.tiles_y;
 	const int warps_per_block = 8;
-	int blocks = c->num_sms * 8;   // persistent CTAs; residency is whatever the register count allows
+	int blocks = c->num_sms * 4;   // persistent CTAs: 4 x 256 threads per SM at <= 64 registers
 	const int max_useful = (n_tiles + warps_per_block - 1) / warps_per_block;
 	if (blocks > max_useful) blocks = max_useful;
 	if (blocks < 1) blocks = 1;
@@ -697,6 +699,16 @@ int hmrm_get_stats(hmrm_ctx *c, hmrm_stats *out) {
 		float ms = 0.f;
 		if (cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) out->kernel_ms = ms;
 	}
+	return HMRM_OK;
+}
+
+int hmrm_get_debug_counters(hmrm_ctx *c, int64_t out[8]) {
+	if (!c || !out) return HMRM_ERR_INVALID;
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
+	DeviceStats ds;
+	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats, sizeof ds, cudaMemcpyDeviceToHost));
+	for (int i = 0; i < 8; ++i) out[i] = (int64_t)ds.dbg[i];
 	return HMRM_OK;
 }
 

@@ -36,6 +36,7 @@ __device__ __forceinline__ bool pixel_selected(const RenderParams &P, int px, in
 struct PixelTally {
 	unsigned long long steps, fetches;
 	unsigned box_hit, surf_hit, cut_off;
+	unsigned dbg[8];
 };
 
 template <bool kStats>
@@ -53,6 +54,11 @@ __device__ __forceinline__ void commit_tally(const RenderParams &P, bool active,
 		const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, mx, off);
 		mx = o > mx ? o : mx;
 		cut |= __shfl_xor_sync(0xFFFFFFFFu, cut, off);
+	}
+	for (int i = 0; i < 8; ++i) {
+		unsigned long long v = t.dbg[i];
+		for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, off);
+		if ((threadIdx.x & 31) == 0 && v) atomicAdd(&P.stats->dbg[i], v);
 	}
 	if ((threadIdx.x & 31) == 0) {
 		atomicAdd(&P.stats->rays, rays);
@@ -79,7 +85,7 @@ __global__ void __launch_bounds__(256) k2_render_brute(const __grid_constant__ R
 		const int py = P.row_begin + ty * 4 + (lane >> 3);
 		const bool active = pixel_selected(P, px, py);
 
-		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u};
+		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u, {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};
 		if (active) {
 			const Ray ray = generate_ray(P, px, py);
 			uint32_t rgba = 0u;

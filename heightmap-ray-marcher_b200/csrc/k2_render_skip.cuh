@@ -71,27 +71,219 @@ __device__ __forceinline__ bool axis_jump(const AxisState &a, double md, double 
 	return binade_tag(end) == a.tag;
 }
 
-// Cell index along one axis from the fixed-point coordinate t = fma(c, 2^k/gw, magic); `c` is x or -y.
-// Returns the reference's (int)(c / grid_width) (main/hmap.cpp:1001-1004), or a value outside [0, dim)
-// when the sample is outside the grid on that side.  `v` receives the raw fixed-point value.
-__device__ __forceinline__ int axis_cell(double c, double t, int k, double gw, int &v) {
-	if (!magic_decode(t, v)) {
-		// |c/gw| >= 2^(31-k) >= map dimension, or NaN: outside the grid either way
-		const bool above = t > HMRM_MAGIC;
-		v = above ? INT_MAX : INT_MIN;
-		return above ? INT_MAX : -1;
-	}
+// How many whole steps can this axis take (closed form) before it leaves its binade?  Estimate only: the
+// caller verifies the end point.  |p| in [2^e, 2^(e+1)).
+__device__ __forceinline__ int steps_to_binade_edge(const AxisState &a) {
+	const double lo_edge = __hiloint2double(__double2hiint(a.p) & 0x7FF00000, 0);   // 2^e
+	const double ap = fabs(a.p), aS = fabs(a.S);
+	const bool toward_zero = (a.S < 0.0) == (a.p > 0.0);
+	const double room = toward_zero ? fsub(ap, lo_edge) : fsub(fmul(lo_edge, 2.0), ap);
+	const double r = fdiv(room, aS);
+	if (!(r < (double)HMRM_JUMP_CAP)) return HMRM_JUMP_CAP;
+	const int n = __double2int_rz(r);
+	return toward_zero ? n : n - 1;
+}
+
+// Fixed-point cell coordinate of one axis.  t = fma(c, 2^k/gw, magic) where c is x or -y.
+// Returns true when the low word v is a valid non-negative decode that is at least one unit away from a
+// cell edge; then |v - 2^k*fl(c/gw)| < 1 implies (int)(c/gw) == v >> k  (main/hmap.cpp:1001-1004).
+__device__ __forceinline__ bool fixed_axis(double t, unsigned mask, int &v) {
+	v = __double2loint(t);
+	return __double2hiint(t) == 0x43380000 && v >= 0 && (((unsigned)v + 1u) & mask) > 1u;
+}
+
+struct MarchPos {
+	int vx, vy;     // fixed-point cell coordinates (estimates when !fast)
+	int cx, cy;     // the reference's cell indices (exact), possibly outside the grid
+	int zq;         // Zq(z)
+	bool fast;      // vx, vy decoded exactly and unambiguously
+};
+
+__device__ __forceinline__ MarchPos locate(const RenderParams &P, double x, double y, double z) {
+	MarchPos r;
+	const int k = P.fx_bits;
 	const unsigned mask = (1u << k) - 1u;
-	if ((((unsigned)v + 1u) & mask) <= 1u) return trunc_cell(fdiv(c, gw));   // within one unit of a cell edge
-	if (v < 0) return (v > -(1 << k)) ? 0 : -1;                                // (int) truncates toward zero
-	return v >> k;
+	const bool okx = fixed_axis(__fma_rn(x, P.fx_scale, HMRM_MAGIC), mask, r.vx);
+	const bool oky = fixed_axis(__fma_rn(y, -P.fx_scale, HMRM_MAGIC), mask, r.vy);
+	r.fast = okx && oky;
+	r.cx = r.vx >> k;
+	r.cy = r.vy >> k;
+	if (!r.fast) {
+		// near a cell edge, negative, huge or NaN: evaluate the reference's own expression
+		if (!okx) {
+			r.cx = trunc_cell(fdiv(x, P.gw));
+			r.vx = (r.cx >= 0 && r.cx < P.map_w) ? (r.cx << k) + (1 << (k - 1)) : 0;
+		}
+		if (!oky) {
+			r.cy = trunc_cell(fdiv(-y, P.gw));
+			r.vy = (r.cy >= 0 && r.cy < P.map_h) ? (r.cy << k) + (1 << (k - 1)) : 0;
+		}
+	}
+	r.zq = zq_of(z, P.zq_scale, P.zq_offset);
+	return r;
 }
 
 template <bool kStats>
-__global__ void __launch_bounds__(256) k2_render_skip(const __grid_constant__ RenderParams P) {
+__device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray, double ex, double ey, double ez,
+                                           uint32_t &rgba, bool &real_hit, int &first_hit, PixelTally &tally) {
+	const int k = P.fx_bits;
+	AxisState ax, ay, az;
+	ax.p = fadd(ex, fmul(P.nudge, ray.dx));           // main/hmap.cpp:998
+	ay.p = fadd(ey, fmul(P.nudge, ray.dy));
+	az.p = fadd(ez, fmul(P.nudge, ray.dz));
+	ax.s = fmul(P.step_dist, ray.dx);                  // :1037
+	ay.s = fmul(P.step_dist, ray.dy);
+	az.s = fmul(P.step_dist, ray.dz);
+	ax.tag = ay.tag = az.tag = INT_MIN;
+	ax.S = ay.S = az.S = 0.0;
+
+	// per-step motion in fixed-point units: estimates only, they never decide a result
+	const float dxf = (float)(ax.s * P.fx_scale);
+	const float dyf = (float)(-ay.s * P.fx_scale);
+	const float dzf = (float)(az.s * P.zq_scale);
+	const float inv_adx = 1.0f / fabsf(dxf), inv_ady = 1.0f / fabsf(dyf), inv_adz = 1.0f / fabsf(dzf);
+	const int cell_exit = (int)fminf(4.0f * fabsf(dzf) + 32.0f, 1.0e9f);
+	const int grid_vx = P.map_w << k, grid_vy = P.map_h << k;   // <= 2^30
+
+	unsigned steps = 0u, fetches = 0u;
+	int level = P.lstart;
+	MarchPos cur = locate(P, ax.p, ay.p, az.p);
+
+	for (;;) {
+		if ((unsigned)cur.cx >= (unsigned)P.map_w || (unsigned)cur.cy >= (unsigned)P.map_h) break;   // :1006-1011
+
+		const int bx = cur.cx >> level, by = cur.cy >> level;
+		const int q = (int)__ldg(P.mip[level] + (size_t)by * (size_t)P.mip_w[level] + (size_t)bx);
+		if (kStats) fetches += 1u;
+
+		int m = 1;
+		int next_level = level;
+		if (cur.zq > q) {
+			// the sample is above every surface value of its level-`level` block: it cannot hit
+			if (level > 0) {
+				const int shift = k + level;
+				int hi_x = (bx + 1) << shift, hi_y = (by + 1) << shift;
+				hi_x = hi_x < grid_vx ? hi_x : grid_vx;
+				hi_y = hi_y < grid_vy ? hi_y : grid_vy;
+				const int edge_x = (dxf > 0.0f) ? (hi_x - cur.vx) : (cur.vx - (bx << shift));
+				const int edge_y = (dyf > 0.0f) ? (hi_y - cur.vy) : (cur.vy - (by << shift));
+				const float est_xy = fminf(__int2float_rz(edge_x) * inv_adx, __int2float_rz(edge_y) * inv_ady);
+				const float est_z = (dzf < 0.0f) ? __int2float_rz(cur.zq - q) * inv_adz : 3.0e38f;
+				const float est = fminf(fminf(est_xy, est_z), (float)HMRM_JUMP_CAP) * 0.999f;
+				m = (est >= 2.0f) ? __float2int_rz(est) : 1;
+				// blocks 4x wider only pay off if z leaves room for 4x more steps; z-limited jumps end just above q
+				if (est_z >= 4.0f * est_xy) next_level = (level + P.lstride <= P.ltop) ? level + P.lstride : level;
+				else if (est_z < est_xy) next_level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
+			}
+			else {
+				if (kStats) tally.dbg[4] += 1u;
+				if (cur.zq - q > cell_exit) next_level = P.lmin;
+			}
+		}
+		else if (level > 0) {
+			level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;   // look closer, no movement
+			if (kStats) tally.dbg[3] += 1u;
+			continue;
+		}
+		else {
+			// finest level: the reference's own test on this cell (main/hmap.cpp:1013-1016)
+			const size_t cell = (size_t)cur.cx + (size_t)cur.cy * (size_t)P.map_w;
+			bool hit = cur.zq < q;
+			if (kStats) tally.dbg[5] += 1u;
+			if (!hit) {
+				hit = az.p < __ldg(P.surf + cell);     // Zq tie: decide in FP64
+				if (kStats) fetches += 1u;
+			}
+			if (hit) {
+				rgba = hit_colour(P, __ldg(P.color + cell));
+				real_hit = true;
+				first_hit = (steps > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)steps;
+				steps += 1u;
+				break;
+			}
+		}
+
+		// ---- advance m samples: closed form when m >= 2, the reference's plain add when m == 1 ----
+		bool jump = false;
+		double md = 1.0;
+		if (m >= 2) {
+			const bool rx = axis_ready(ax), ry = axis_ready(ay), rz = axis_ready(az);
+			jump = rx && ry && rz && cur.fast;
+			if (jump && m == HMRM_JUMP_CAP && ax.S == 0.0 && ay.S == 0.0 && !(az.S < 0.0)) {
+				tally.cut_off = 1u;            // cannot move sideways, not coming down: the reference never ends
+				steps += 1u;
+				break;
+			}
+			md = small_int_to_double(m);
+		}
+		double nx = jump ? __fma_rn(md, ax.S, ax.p) : fadd(ax.p, ax.s);
+		double ny = jump ? __fma_rn(md, ay.S, ay.p) : fadd(ay.p, ay.s);
+		double nz = jump ? __fma_rn(md, az.S, az.p) : fadd(az.p, az.s);
+		MarchPos nxt = locate(P, nx, ny, nz);
+		if (jump) {
+			// (1) same binades, (3) end point in the same block (one unit clear of its edges), in the grid, above q
+			const int shift = k + level;
+			int hi_x = (bx + 1) << shift, hi_y = (by + 1) << shift;
+			hi_x = hi_x < grid_vx ? hi_x : grid_vx;
+			hi_y = hi_y < grid_vy ? hi_y : grid_vy;
+			const int lo_x = bx << shift, lo_y = by << shift;
+			bool in_binade = binade_tag(nx) == ax.tag && binade_tag(ny) == ay.tag && binade_tag(nz) == az.tag;
+			bool ok = in_binade && nxt.fast && nxt.vx - lo_x >= 1 && hi_x - nxt.vx >= 2 && nxt.vy - lo_y >= 1 &&
+			          hi_y - nxt.vy >= 2 && nxt.zq > q;
+			if (!in_binade) {
+				// some axis would leave its binade: go exactly as far as the binade allows, the next plain step crosses
+				int m2 = m;
+				if (binade_tag(nx) != ax.tag) m2 = min(m2, steps_to_binade_edge(ax));
+				if (binade_tag(ny) != ay.tag) m2 = min(m2, steps_to_binade_edge(ay));
+				if (binade_tag(nz) != az.tag) m2 = min(m2, steps_to_binade_edge(az));
+				if (m2 >= 2 && m2 < m) {
+					m = m2;
+					md = small_int_to_double(m);
+					nx = __fma_rn(md, ax.S, ax.p);
+					ny = __fma_rn(md, ay.S, ay.p);
+					nz = __fma_rn(md, az.S, az.p);
+					nxt = locate(P, nx, ny, nz);
+					ok = binade_tag(nx) == ax.tag && binade_tag(ny) == ay.tag && binade_tag(nz) == az.tag && nxt.fast &&
+					     nxt.vx - lo_x >= 1 && hi_x - nxt.vx >= 2 && nxt.vy - lo_y >= 1 && hi_y - nxt.vy >= 2 && nxt.zq > q;
+					next_level = level;
+				}
+			}
+			if (!ok) {
+				if (kStats) tally.dbg[6] += 1u;
+				jump = false;
+				nx = fadd(ax.p, ax.s);
+				ny = fadd(ay.p, ay.s);
+				nz = fadd(az.p, az.s);
+				nxt = locate(P, nx, ny, nz);
+				next_level = level;
+			}
+		}
+		if (!jump) {
+			m = 1;
+			if (nx == ax.p && ny == ay.p && !(nz < az.p)) {
+				tally.cut_off = 1u;            // same condition on the plain step
+				steps += 1u;
+				break;
+			}
+		}
+		if (kStats) {
+			if (jump) { tally.dbg[0] += 1u; tally.dbg[1] += (unsigned)m; }
+			else if (level > 0) tally.dbg[2] += 1u;
+			if (!nxt.fast) tally.dbg[7] += 1u;
+		}
+		ax.p = nx; ay.p = ny; az.p = nz;
+		cur = nxt;
+		steps += (unsigned)m;
+		level = next_level;
+	}
+	tally.steps = steps;
+	tally.fetches = fetches;
+}
+
+template <bool kStats>
+__global__ void __launch_bounds__(256, 4) k2_render_skip(const __grid_constant__ RenderParams P) {
 	const int lane = threadIdx.x & 31;
 	const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
-	const int k = P.fx_bits;
 
 	for (;;) {
 		const unsigned tile = next_tile(P.tile_counter);
@@ -102,7 +294,7 @@ __global__ void __launch_bounds__(256) k2_render_skip(const __grid_constant__ Re
 		const int py = P.row_begin + ty * 4 + (lane >> 3);
 		const bool active = pixel_selected(P, px, py);
 
-		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u};
+		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u, {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};
 		if (active) {
 			const Ray ray = generate_ray(P, px, py);
 			uint32_t rgba = 0u;
@@ -112,148 +304,7 @@ __global__ void __launch_bounds__(256) k2_render_skip(const __grid_constant__ Re
 			if (box_entry(P, ray, ex, ey, ez)) {
 				tally.box_hit = 1u;
 				first_hit = -2;
-				AxisState ax, ay, az;
-				ax.p = fadd(ex, fmul(P.nudge, ray.dx));           // main/hmap.cpp:998
-				ay.p = fadd(ey, fmul(P.nudge, ray.dy));
-				az.p = fadd(ez, fmul(P.nudge, ray.dz));
-				ax.s = fmul(P.step_dist, ray.dx);                  // :1037
-				ay.s = fmul(P.step_dist, ray.dy);
-				az.s = fmul(P.step_dist, ray.dz);
-				ax.tag = ay.tag = az.tag = INT_MIN;
-				ax.S = ay.S = az.S = 0.0;
-
-				// per-step motion in fixed-point units (estimates only; never decide a result)
-				const float dxf = (float)(ax.s * P.fx_scale);
-				const float dyf = (float)(-ay.s * P.fx_scale);
-				const float dzf = (float)(az.s * P.zq_scale);
-				const float inv_adx = 1.0f / fabsf(dxf), inv_ady = 1.0f / fabsf(dyf), inv_adz = 1.0f / fabsf(dzf);
-
-				unsigned long long steps = 0ULL, fetches = 0ULL;
-				int level = P.lmin + 2 * P.lstride;
-				if (level > P.ltop) level = P.ltop;
-
-				int vx, vy;
-				int cx = axis_cell(ax.p, __fma_rn(ax.p, P.fx_scale, HMRM_MAGIC), k, P.gw, vx);
-				int cy = axis_cell(-ay.p, __fma_rn(ay.p, -P.fx_scale, HMRM_MAGIC), k, P.gw, vy);
-				int zq = zq_of(az.p, P.zq_scale, P.zq_offset);
-
-				for (;;) {
-					if (cx < 0 || cy < 0 || cx >= P.map_w || cy >= P.map_h) break;   // :1006-1011
-
-					bool stepped = false;
-					while (level >= P.lmin) {
-						const int shift = k + level;
-						const int bx = cx >> level, by = cy >> level;
-						const int qmax = (int)__ldg(P.mip[level] + (size_t)by * (size_t)P.mip_w[level] + (size_t)bx);
-						fetches += 1ULL;
-						if (zq <= qmax) {
-							level -= P.lstride;      // not clear of this block: look closer
-							continue;
-						}
-						// Sample is above everything in block (bx,by): it cannot hit.  How far can we go?
-						float est = (float)HMRM_JUMP_CAP;
-						if (vx != INT_MAX && vx != INT_MIN) {
-							const int edge = (dxf > 0.0f) ? (((bx + 1) << shift) - vx) : (vx - (bx << shift));
-							est = fminf(est, __int2float_rz(edge) * inv_adx);
-						}
-						if (vy != INT_MAX && vy != INT_MIN) {
-							const int edge = (dyf > 0.0f) ? (((by + 1) << shift) - vy) : (vy - (by << shift));
-							est = fminf(est, __int2float_rz(edge) * inv_ady);
-						}
-						if (dzf < 0.0f) est = fminf(est, __int2float_rz(zq - qmax) * inv_adz);
-						int m = (est >= 2.0f) ? __float2int_rz(est) : 1;
-						if (m >= 2) {
-							// evaluate all three (each may need its increment refreshed)
-							const bool rx = axis_ready(ax), ry = axis_ready(ay), rz = axis_ready(az);
-							if (!(rx && ry && rz)) m = 1;
-						}
-
-						while (m >= 2) {
-							const double md = small_int_to_double(m);
-							double nx, ny, nz;
-							if (axis_jump(ax, md, nx) && axis_jump(ay, md, ny) && axis_jump(az, md, nz)) {
-								// a ray that cannot move sideways and is not coming down never ends (reference hangs)
-								if (ax.S == 0.0 && ay.S == 0.0 && !(az.S < 0.0)) {
-									tally.cut_off = 1u;
-									steps += 1ULL;
-									m = -1;
-									break;
-								}
-								int wx, wy;
-								const bool okx = magic_decode(__fma_rn(nx, P.fx_scale, HMRM_MAGIC), wx);
-								const bool oky = magic_decode(__fma_rn(ny, -P.fx_scale, HMRM_MAGIC), wy);
-								const int wz = zq_of(nz, P.zq_scale, P.zq_offset);
-								// (3): end point inside the same block (with the +-1 unit uncertainty), in the grid, above the block
-								if (okx && oky && wx >= 1 && wy >= 1 && ((wx - 1) >> shift) == bx && ((wx + 1) >> shift) == bx &&
-								    ((wy - 1) >> shift) == by && ((wy + 1) >> shift) == by && ((wx + 1) >> k) < P.map_w &&
-								    ((wy + 1) >> k) < P.map_h && wz > qmax) {
-									ax.p = nx; ay.p = ny; az.p = nz;
-									steps += (unsigned long long)m;
-									int dummy;
-									cx = axis_cell(nx, __fma_rn(nx, P.fx_scale, HMRM_MAGIC), k, P.gw, dummy);
-									cy = axis_cell(-ny, __fma_rn(ny, -P.fx_scale, HMRM_MAGIC), k, P.gw, dummy);
-									vx = wx; vy = wy; zq = wz;
-									break;
-								}
-							}
-							m >>= 1;
-						}
-						if (m < 0) break;   // cut off
-						if (m >= 2) {
-							// jumped; the end point is the next sample to examine, one level coarser
-							level += P.lstride;
-							if (level > P.ltop) level -= P.lstride;
-						}
-						else {
-							// plain single step (always exact), no cell test needed for the current sample
-							const double nx = fadd(ax.p, ax.s), ny = fadd(ay.p, ay.s), nz = fadd(az.p, az.s);
-							if (nx == ax.p && ny == ay.p && !(nz < az.p)) {
-								tally.cut_off = 1u;
-								steps += 1ULL;
-								m = -1;
-								break;
-							}
-							ax.p = nx; ay.p = ny; az.p = nz;
-							steps += 1ULL;
-							cx = axis_cell(nx, __fma_rn(nx, P.fx_scale, HMRM_MAGIC), k, P.gw, vx);
-							cy = axis_cell(-ny, __fma_rn(ny, -P.fx_scale, HMRM_MAGIC), k, P.gw, vy);
-							zq = zq_of(nz, P.zq_scale, P.zq_offset);
-						}
-						stepped = true;
-						break;
-					}
-					if (tally.cut_off) break;
-					if (stepped) continue;
-
-					// finest level: the reference's own test on this cell (main/hmap.cpp:1013-1016)
-					const size_t cell = (size_t)cx + (size_t)cy * (size_t)P.map_w;
-					const int q = (int)__ldg(P.q0 + cell);
-					fetches += 1ULL;
-					steps += 1ULL;
-					bool hit = zq < q;
-					if (zq == q) {
-						hit = az.p < __ldg(P.surf + cell);
-						fetches += 1ULL;
-					}
-					if (hit) {
-						rgba = hit_colour(P, __ldg(P.color + cell));
-						real_hit = true;
-						first_hit = (steps - 1ULL > 0x7FFFFFFFULL) ? 0x7FFFFFFF : (int)(steps - 1ULL);
-						break;
-					}
-					const double nx = fadd(ax.p, ax.s), ny = fadd(ay.p, ay.s), nz = fadd(az.p, az.s);
-					if (nx == ax.p && ny == ay.p && !(nz < az.p)) {
-						tally.cut_off = 1u;
-						break;
-					}
-					ax.p = nx; ay.p = ny; az.p = nz;
-					cx = axis_cell(nx, __fma_rn(nx, P.fx_scale, HMRM_MAGIC), k, P.gw, vx);
-					cy = axis_cell(-ny, __fma_rn(ny, -P.fx_scale, HMRM_MAGIC), k, P.gw, vy);
-					zq = zq_of(nz, P.zq_scale, P.zq_offset);
-					level = P.lmin;
-				}
-				tally.steps = steps;
-				tally.fetches = fetches;
+				march_skip<kStats>(P, ray, ex, ey, ez, rgba, real_hit, first_hit, tally);
 			}
 			if (!real_hit) rgba = miss_colour(P, ray.dz);
 			else tally.surf_hit = 1u;

@@ -16,6 +16,7 @@ struct DeviceStats {
 	unsigned long long max_steps;
 	unsigned int status;           // HMRM_ERR_NONTERMINATING if a ray was cut off
 	unsigned int pad;
+	unsigned long long dbg[8];     // traversal diagnostics (stats mode only), see hmrm_get_debug_counters
 };
 
 struct RenderParams {
@@ -50,7 +51,8 @@ struct RenderParams {
 	double fx_scale;               // fl(2^fx_bits / grid_width): cell coordinate in 2^-fx_bits cell units
 	double zq_scale, zq_offset;    // Zq(z) = low32(fma(z, zq_scale, zq_offset)); same function quantises surf in K1
 	int fx_bits;                   // fractional bits of the fixed-point cell coordinate
-	int lmin, lstride, ltop;       // mip levels used this frame: lmin, lmin+lstride, ... <= ltop
+	int lmin, lstride, ltop;       // mip levels used this frame: lmin, lmin+lstride, ... <= ltop (0 = cell test)
+	int lstart;                    // level of a ray's first test
 	const uint16_t *q0;            // Zq(surf) per cell, row-major [map_h][map_w]
 	const uint16_t *mip[16];       // mip[l]: max of q0 over 2^l x 2^l blocks, row-major, pitch mip_w[l]; mip[0] == q0
 	int mip_w[16];

@@ -121,6 +121,10 @@ int hmrm_render_async(hmrm_ctx *ctx, const hmrm_frame *f, uint8_t *rgba_out);
 int hmrm_wait(hmrm_ctx *ctx);
 
 int hmrm_get_stats(hmrm_ctx *ctx, hmrm_stats *out);            /* of the last render */
+/* traversal diagnostics of the last HMRM_FLAG_STATS render with the skip traversal: [0] jumps, [1] samples covered
+ * by jumps, [2] single steps above a mip block, [3] level descents, [4] cell tests above the cell, [5] cell tests at or
+ * below the quantised height, [6] refused jumps, [7] samples located through the exact divide */
+int hmrm_get_debug_counters(hmrm_ctx *ctx, int64_t out[8]);
 int hmrm_get_step_index(hmrm_ctx *ctx, int32_t *step_index);   /* int32 [H][W]: first-hit sample index,
                                                                   -1 box missed, -2 no surface hit */
 

@@ -35,4 +35,8 @@ for i in range(args.frames):
     print(f"frame {args.first + i}: kernel {st.kernel_ms:.3f} ms" +
           (f" rays {st.rays} box {st.box_hits} surf {st.surf_hits} steps {st.steps} fetches {st.fetches} max {st.max_steps}"
            if args.stats else ""))
+    if args.stats:
+        d = r.debug_counters()
+        print("   jumps %d (covering %d samples, %.1f/jump) plain-above %d descents %d cell-above %d cell-below %d refused %d slow-locate %d"
+              % (d[0], d[1], d[1] / max(d[0], 1), d[2], d[3], d[4], d[5], d[6], d[7]))
 r.close()
