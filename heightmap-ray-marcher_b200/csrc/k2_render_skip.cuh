@@ -123,6 +123,12 @@ __device__ __forceinline__ MarchPos locate(const RenderParams &P, double x, doub
 	return r;
 }
 
+// Per-level view of "how far can this sample go": block bounds in fixed point and step estimates.
+struct LevelEst {
+	int lo_x, hi_x, lo_y, hi_y;   // block extent (clipped to the grid) in fixed-point units
+	float est_xy, est_z;          // steps until the block edge / until Zq(z) could reach q (estimates)
+};
+
 template <bool kStats>
 __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray, double ex, double ey, double ez,
                                            uint32_t &rgba, bool &real_hit, int &first_hit, PixelTally &tally) {
@@ -145,48 +151,68 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 	const int cell_exit = (int)fminf(4.0f * fabsf(dzf) + 32.0f, 1.0e9f);
 	const int grid_vx = P.map_w << k, grid_vy = P.map_h << k;   // <= 2^30
 
+	auto probe = [&](int level, int cx, int cy) -> int {
+		return (int)__ldg(P.mip[level] + (size_t)(cy >> level) * (size_t)P.mip_w[level] + (size_t)(cx >> level));
+	};
+	auto estimate = [&](int level, const MarchPos &c, int q) -> LevelEst {
+		LevelEst e;
+		const int shift = k + level;
+		const int bx = c.cx >> level, by = c.cy >> level;
+		e.lo_x = bx << shift;
+		e.lo_y = by << shift;
+		e.hi_x = min((bx + 1) << shift, grid_vx);
+		e.hi_y = min((by + 1) << shift, grid_vy);
+		const int edge_x = (dxf > 0.0f) ? (e.hi_x - c.vx) : (c.vx - e.lo_x);
+		const int edge_y = (dyf > 0.0f) ? (e.hi_y - c.vy) : (c.vy - e.lo_y);
+		e.est_xy = fminf(__int2float_rz(edge_x) * inv_adx, __int2float_rz(edge_y) * inv_ady);
+		e.est_z = (dzf < 0.0f) ? __int2float_rz(c.zq - q) * inv_adz : 3.0e38f;
+		return e;
+	};
+
 	unsigned steps = 0u, fetches = 0u;
 	int level = P.lstart;
 	MarchPos cur = locate(P, ax.p, ay.p, az.p);
 
-	for (;;) {
-		if ((unsigned)cur.cx >= (unsigned)P.map_w || (unsigned)cur.cy >= (unsigned)P.map_h) break;   // :1006-1011
-
-		const int bx = cur.cx >> level, by = cur.cy >> level;
-		const int q = (int)__ldg(P.mip[level] + (size_t)by * (size_t)P.mip_w[level] + (size_t)bx);
+	while ((unsigned)cur.cx < (unsigned)P.map_w && (unsigned)cur.cy < (unsigned)P.map_h) {   // :1006-1011
+		// ---- A: find a level whose block this sample clears (descend), or reach the cell itself ----
+		int q = probe(level, cur.cx, cur.cy);
 		if (kStats) fetches += 1u;
+		while (cur.zq <= q && level > 0) {
+			level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
+			q = probe(level, cur.cx, cur.cy);
+			if (kStats) { fetches += 1u; tally.dbg[3] += 1u; }
+		}
 
 		int m = 1;
 		int next_level = level;
+		LevelEst e;
+		e.lo_x = e.lo_y = e.hi_x = e.hi_y = 0;
 		if (cur.zq > q) {
-			// the sample is above every surface value of its level-`level` block: it cannot hit
+			// above every surface value of the block: the sample cannot hit
 			if (level > 0) {
-				const int shift = k + level;
-				int hi_x = (bx + 1) << shift, hi_y = (by + 1) << shift;
-				hi_x = hi_x < grid_vx ? hi_x : grid_vx;
-				hi_y = hi_y < grid_vy ? hi_y : grid_vy;
-				const int edge_x = (dxf > 0.0f) ? (hi_x - cur.vx) : (cur.vx - (bx << shift));
-				const int edge_y = (dyf > 0.0f) ? (hi_y - cur.vy) : (cur.vy - (by << shift));
-				const float est_xy = fminf(__int2float_rz(edge_x) * inv_adx, __int2float_rz(edge_y) * inv_ady);
-				const float est_z = (dzf < 0.0f) ? __int2float_rz(cur.zq - q) * inv_adz : 3.0e38f;
-				const float est = fminf(fminf(est_xy, est_z), (float)HMRM_JUMP_CAP) * 0.999f;
+				e = estimate(level, cur, q);
+				// climb while z leaves room for (much) wider blocks and the wider block is cleared too
+				while (e.est_z >= 4.0f * e.est_xy && level + P.lstride <= P.ltop) {
+					const int q2 = probe(level + P.lstride, cur.cx, cur.cy);
+					if (kStats) fetches += 1u;
+					if (cur.zq <= q2) break;
+					level += P.lstride;
+					q = q2;
+					e = estimate(level, cur, q);
+				}
+				const float est = fminf(fminf(e.est_xy, e.est_z), (float)HMRM_JUMP_CAP) * 0.999f;
 				m = (est >= 2.0f) ? __float2int_rz(est) : 1;
-				// blocks 4x wider only pay off if z leaves room for 4x more steps; z-limited jumps end just above q
-				if (est_z >= 4.0f * est_xy) next_level = (level + P.lstride <= P.ltop) ? level + P.lstride : level;
-				else if (est_z < est_xy) next_level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
+				next_level = level;
+				// a z-limited jump ends just above q: the next sample will need a finer block
+				if (e.est_z < e.est_xy) next_level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
 			}
 			else {
 				if (kStats) tally.dbg[4] += 1u;
 				if (cur.zq - q > cell_exit) next_level = P.lmin;
 			}
 		}
-		else if (level > 0) {
-			level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;   // look closer, no movement
-			if (kStats) tally.dbg[3] += 1u;
-			continue;
-		}
 		else {
-			// finest level: the reference's own test on this cell (main/hmap.cpp:1013-1016)
+			// level 0 and not above: the reference's own test on this cell (main/hmap.cpp:1013-1016)
 			const size_t cell = (size_t)cur.cx + (size_t)cur.cy * (size_t)P.map_w;
 			bool hit = cur.zq < q;
 			if (kStats) tally.dbg[5] += 1u;
@@ -203,7 +229,7 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 			}
 		}
 
-		// ---- advance m samples: closed form when m >= 2, the reference's plain add when m == 1 ----
+		// ---- C: advance m samples: closed form when m >= 2, the reference's plain add when m == 1 ----
 		bool jump = false;
 		double md = 1.0;
 		if (m >= 2) {
@@ -222,14 +248,9 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 		MarchPos nxt = locate(P, nx, ny, nz);
 		if (jump) {
 			// (1) same binades, (3) end point in the same block (one unit clear of its edges), in the grid, above q
-			const int shift = k + level;
-			int hi_x = (bx + 1) << shift, hi_y = (by + 1) << shift;
-			hi_x = hi_x < grid_vx ? hi_x : grid_vx;
-			hi_y = hi_y < grid_vy ? hi_y : grid_vy;
-			const int lo_x = bx << shift, lo_y = by << shift;
 			bool in_binade = binade_tag(nx) == ax.tag && binade_tag(ny) == ay.tag && binade_tag(nz) == az.tag;
-			bool ok = in_binade && nxt.fast && nxt.vx - lo_x >= 1 && hi_x - nxt.vx >= 2 && nxt.vy - lo_y >= 1 &&
-			          hi_y - nxt.vy >= 2 && nxt.zq > q;
+			bool ok = in_binade && nxt.fast && nxt.vx - e.lo_x >= 1 && e.hi_x - nxt.vx >= 2 && nxt.vy - e.lo_y >= 1 &&
+			          e.hi_y - nxt.vy >= 2 && nxt.zq > q;
 			if (!in_binade) {
 				// some axis would leave its binade: go exactly as far as the binade allows, the next plain step crosses
 				int m2 = m;
@@ -244,7 +265,8 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 					nz = __fma_rn(md, az.S, az.p);
 					nxt = locate(P, nx, ny, nz);
 					ok = binade_tag(nx) == ax.tag && binade_tag(ny) == ay.tag && binade_tag(nz) == az.tag && nxt.fast &&
-					     nxt.vx - lo_x >= 1 && hi_x - nxt.vx >= 2 && nxt.vy - lo_y >= 1 && hi_y - nxt.vy >= 2 && nxt.zq > q;
+					     nxt.vx - e.lo_x >= 1 && e.hi_x - nxt.vx >= 2 && nxt.vy - e.lo_y >= 1 && e.hi_y - nxt.vy >= 2 &&
+					     nxt.zq > q;
 					next_level = level;
 				}
 			}
@@ -260,8 +282,9 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 		}
 		if (!jump) {
 			m = 1;
-			if (nx == ax.p && ny == ay.p && !(nz < az.p)) {
-				tally.cut_off = 1u;            // same condition on the plain step
+			// a sample that does not move sideways keeps its fixed-point coordinates: test those first
+			if (nxt.vx == cur.vx && nxt.vy == cur.vy && nx == ax.p && ny == ay.p && !(nz < az.p)) {
+				tally.cut_off = 1u;            // the reference would loop forever
 				steps += 1u;
 				break;
 			}
