@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -54,6 +55,7 @@ struct hmrm_ctx {
 	double lum[3], min_height, max_height, max_surf, min_surf;
 	// conservative fixed-point view for the skip traversal
 	uint16_t *d_mip;             // levels 0..mip_levels-1 back to back; level 0 = Zq(surf) per cell
+	uint16_t *d_dil;             // levels 1..: 3x3-block dilation of d_mip's level (what the traversal reads)
 	size_t mip_offset[16];
 	int mip_w[16], mip_h[16];
 	int mip_levels;
@@ -122,7 +124,9 @@ void free_maps(hmrm_ctx *c) {
 	cudaFree(c->d_color);
 	cudaFree(c->d_surf);
 	cudaFree(c->d_mip);
+	cudaFree(c->d_dil);
 	c->d_mip = NULL;
+	c->d_dil = NULL;
 	c->d_rgb = NULL;
 	c->d_color = NULL;
 	c->d_surf = NULL;
@@ -157,6 +161,7 @@ int alloc_maps(hmrm_ctx *c, int32_t w, int32_t h) {
 	}
 	c->mip_levels = levels;
 	HMRM_CUDA(c, cudaMalloc(&c->d_mip, total * 2));
+	if (levels > 1) HMRM_CUDA(c, cudaMalloc(&c->d_dil, (total - c->mip_offset[1]) * 2));
 	c->map_w = w;
 	c->map_h = h;
 	return HMRM_OK;
@@ -346,13 +351,21 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		const double step_cells = f->step_dist / f->grid_width;
 		int lmin = 1;
 		while (lmin < P.ltop && (double)(1 << lmin) < 2.0 * step_cells) lmin += 1;
+		// tuning knobs for experiments (never affect results, only how many fetches are issued)
+		const char *e_bias = std::getenv("HMRM_LMIN_BIAS"), *e_stride = std::getenv("HMRM_LSTRIDE");
+		const char *e_exit = std::getenv("HMRM_CELL_EXIT");
+		if (e_bias) lmin += std::atoi(e_bias);
+		if (lmin < 1) lmin = 1;
+		if (lmin > P.ltop) lmin = P.ltop;
 		P.lmin = lmin;
-		P.lstride = 2;
+		P.lstride = e_stride ? std::atoi(e_stride) : 2;
+		if (P.lstride < 1) P.lstride = 1;
+		P.cell_exit_scale = e_exit ? (float)std::atof(e_exit) : 4.0f;
 		P.lstart = lmin + 2 * P.lstride <= P.ltop ? lmin + 2 * P.lstride : lmin;
 		if (P.fx_bits < 1) traversal = HMRM_TRAVERSAL_BRUTE;
 		P.q0 = c->d_mip;
 		for (int l = 0; l < 16; ++l) {
-			P.mip[l] = (l < c->mip_levels) ? c->d_mip + c->mip_offset[l] : NULL;
+			P.mip[l] = (l < c->mip_levels) ? (l == 0 ? c->d_mip : c->d_dil + (c->mip_offset[l] - c->mip_offset[1])) : NULL;
 			P.mip_w[l] = (l < c->mip_levels) ? c->mip_w[l] : 0;
 		}
 		if (!std::isfinite(P.fx_scale)) traversal = HMRM_TRAVERSAL_BRUTE;
@@ -434,6 +447,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->max_height = 10.0;
 	c->max_surf = c->min_surf = 0.0;
 	c->d_mip = NULL;
+	c->d_dil = NULL;
 	c->mip_levels = 0;
 	c->zq_scale = 1.0;
 	c->zq_offset = HMRM_MAGIC;
@@ -581,6 +595,10 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 	for (int l = 1; l < c->mip_levels; ++l) {
 		k1_mip_reduce<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_mip + c->mip_offset[l - 1], c->mip_w[l - 1],
 		                                                      c->mip_h[l - 1], c->d_mip + c->mip_offset[l],
+		                                                      c->mip_w[l], c->mip_h[l]);
+		HMRM_CUDA(c, cudaGetLastError());
+		k1_mip_dilate<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_mip + c->mip_offset[l],
+		                                                      c->d_dil + (c->mip_offset[l] - c->mip_offset[1]),
 		                                                      c->mip_w[l], c->mip_h[l]);
 		HMRM_CUDA(c, cudaGetLastError());
 	}

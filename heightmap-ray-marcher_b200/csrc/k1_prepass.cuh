@@ -131,6 +131,29 @@ __global__ void __launch_bounds__(256) k1_mip_reduce(const uint16_t *__restrict_
 	}
 }
 
+// dst[y][x] = max of src over the 3x3 neighbourhood (clipped): a sample that clears dst clears the block it is in
+// AND the eight blocks around it, so a jump may run on into the neighbouring blocks instead of stopping at an edge.
+__global__ void __launch_bounds__(256) k1_mip_dilate(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst,
+                                                     int w, int h) {
+	const long long n = (long long)w * h;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
+		const int x = (int)(p % w), y = (int)(p / w);
+		uint16_t m = 0;
+		for (int dy = -1; dy <= 1; ++dy) {
+			const int yy = y + dy;
+			if (yy < 0 || yy >= h) continue;
+			for (int dx = -1; dx <= 1; ++dx) {
+				const int xx = x + dx;
+				if (xx < 0 || xx >= w) continue;
+				const uint16_t v = src[(size_t)yy * w + xx];
+				m = v > m ? v : m;
+			}
+		}
+		dst[p] = m;
+	}
+}
+
 } // namespace hmrm
 
 #endif

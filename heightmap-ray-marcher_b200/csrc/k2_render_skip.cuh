@@ -148,7 +148,7 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 	const float dyf = (float)(-ay.s * P.fx_scale);
 	const float dzf = (float)(az.s * P.zq_scale);
 	const float inv_adx = 1.0f / fabsf(dxf), inv_ady = 1.0f / fabsf(dyf), inv_adz = 1.0f / fabsf(dzf);
-	const int cell_exit = (int)fminf(4.0f * fabsf(dzf) + 32.0f, 1.0e9f);
+	const int cell_exit = (int)fminf(P.cell_exit_scale * fabsf(dzf) + 32.0f, 1.0e9f);
 	const int grid_vx = P.map_w << k, grid_vy = P.map_h << k;   // <= 2^30
 
 	auto probe = [&](int level, int cx, int cy) -> int {
@@ -158,10 +158,11 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 		LevelEst e;
 		const int shift = k + level;
 		const int bx = c.cx >> level, by = c.cy >> level;
-		e.lo_x = bx << shift;
-		e.lo_y = by << shift;
-		e.hi_x = min((bx + 1) << shift, grid_vx);
-		e.hi_y = min((by + 1) << shift, grid_vy);
+		// levels >= 1 hold the 3x3-dilated maximum: the cleared region is the block and its eight neighbours
+		e.lo_x = max(bx - 1, 0) << shift;
+		e.lo_y = max(by - 1, 0) << shift;
+		e.hi_x = (int)min((unsigned)(bx + 2) << shift, (unsigned)grid_vx);
+		e.hi_y = (int)min((unsigned)(by + 2) << shift, (unsigned)grid_vy);
 		const int edge_x = (dxf > 0.0f) ? (e.hi_x - c.vx) : (c.vx - e.lo_x);
 		const int edge_y = (dyf > 0.0f) ? (e.hi_y - c.vy) : (c.vy - e.lo_y);
 		e.est_xy = fminf(__int2float_rz(edge_x) * inv_adx, __int2float_rz(edge_y) * inv_ady);

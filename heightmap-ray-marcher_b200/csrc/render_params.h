@@ -53,6 +53,7 @@ struct RenderParams {
 	int fx_bits;                   // fractional bits of the fixed-point cell coordinate
 	int lmin, lstride, ltop;       // mip levels used this frame: lmin, lmin+lstride, ... <= ltop (0 = cell test)
 	int lstart;                    // level of a ray's first test
+	float cell_exit_scale;         // leave cell-by-cell mode when Zq(z) - q exceeds this many steps of descent
 	const uint16_t *q0;            // Zq(surf) per cell, row-major [map_h][map_w]
 	const uint16_t *mip[16];       // mip[l]: max of q0 over 2^l x 2^l blocks, row-major, pitch mip_w[l]; mip[0] == q0
 	int mip_w[16];
