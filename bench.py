@@ -264,17 +264,27 @@ def ours_arm(args, wl) -> None:
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+
+    def keep_busy(seconds: float) -> None:
+        """Same kernel, same frames, back to back (untimed): the timed region is ~10 ms, far below nvidia-smi's
+        sampling period, so the clocks are sampled over this load window that brackets it."""
+        t_end = time.perf_counter() + seconds
+        while time.perf_counter() < t_end:
+            for n in my_frames:
+                r.render_device(frame_of(n), d_out, stream.cuda_stream)
+            stream.synchronize()
+
+    t_wall0 = time.perf_counter()
+    keep_busy(0.5)
     barrier()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
     ev0.record(stream)
     for n in my_frames:
         r.render_device(frame_of(n), d_out, stream.cuda_stream)
     ev1.record(stream)
     barrier()
-    t_wall1 = time.perf_counter()
     dev_ms = ev0.elapsed_time(ev1)
+    keep_busy(0.4)
 
     # ---- e2e: the user's call — host output buffer, D2H inside the timed region ----
     for n in warm_frames:
@@ -287,6 +297,8 @@ def ours_arm(args, wl) -> None:
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
     clocks = sampler.stop(t_wall0, time.perf_counter()) if rank == 0 else None
+    if clocks is not None:
+        clocks["window"] = "0.9 s of the timed kernel running back to back around the timed region"
 
     # ---- per-kernel duration for the roofline: CUDA events around K2 inside the library ----
     kernel_ms = []

@@ -14,6 +14,8 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libhmrm.so"
+HOST = PKG / "host"
+HMAP = PKG / "hmap"          # the reference's binary name; headless host over libhmrm.so
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -30,6 +32,18 @@ def sources() -> list[Path]:
 
 def deps() -> list[Path]:
     return sorted(list(CSRC.glob("*")) + [PKG.parent / "include" / "hmrm.h", Path(__file__)])
+
+
+def build_hmap(force: bool = False) -> Path:
+    """g++ host (config grammar, image I/O, CLI) linked against libhmrm.so."""
+    srcs = sorted(HOST.glob("*.cpp"))
+    newest = max(p.stat().st_mtime for p in list(HOST.glob("*")) + [PKG.parent / "include" / "hmrm.h", LIB])
+    if not force and HMAP.exists() and HMAP.stat().st_mtime >= newest:
+        return HMAP
+    cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-ffp-contract=off", "-o", str(HMAP), *[str(s) for s in srcs],
+           "-L", str(PKG), "-lhmrm", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN"]
+    subprocess.run(cmd, check=True, cwd=str(PKG))
+    return HMAP
 
 
 def is_stale() -> bool:
@@ -52,4 +66,6 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
 
 if __name__ == "__main__":
     build_lib(force="--force" in sys.argv, verbose=True)
+    build_hmap(force="--force" in sys.argv)
     print(LIB)
+    print(HMAP)

@@ -10,6 +10,7 @@
 //
 //   ref_harness heights <rgb8.raw> W H lr lg lb min max <out.f64>
 //   ref_harness kat < queries > answers       (hex-float text protocol)
+//   ref_harness decode <image> 3|4 <out.raw>  (stbi_load exactly as main/hmap.cpp:320-321 / :341-342 call it)
 //
 // kat queries (all numbers C99 hex floats, "%la"):
 //   R proj px py pz hang vang hfov ow W H w h   -> ray through the reference's own
@@ -107,7 +108,25 @@ static int cmd_kat() {
 	return 0;
 }
 
+static int cmd_decode(int argc, char **argv) {
+	if (argc != 5) return 2;
+	int w = 0, h = 0, n = 0;
+	const int comp = std::atoi(argv[3]);
+	unsigned char *px = stbi_load(argv[2], &w, &h, &n, comp);
+	if (px == NULL) {
+		std::printf("FAIL\n");
+		return 0;
+	}
+	FILE *f = std::fopen(argv[4], "wb");
+	std::fwrite(px, 1, (size_t)w * (size_t)h * (size_t)comp, f);
+	std::fclose(f);
+	std::printf("%d %d %d\n", w, h, comp);
+	stbi_image_free(px);
+	return 0;
+}
+
 int main(int argc, char **argv) {
+	if (argc >= 2 && std::strcmp(argv[1], "decode") == 0) return cmd_decode(argc, argv);
 	if (argc >= 2 && std::strcmp(argv[1], "heights") == 0) return cmd_heights(argc, argv);
 	if (argc >= 2 && std::strcmp(argv[1], "kat") == 0) return cmd_kat();
 	std::fprintf(stderr, "usage: ref_harness heights ...|kat\n");
