@@ -41,6 +41,9 @@ WORKLOADS = {
                           desc="spherical 1920x1080 over a 4096^2 fBm heightmap (BASELINE configs[1])"),
     "ortho4k": dict(log2n=13, W=3840, H=2160, projection=3, step_dist=0.00625, frames=240,
                     desc="orthographic 3840x2160 over an 8192^2 fBm heightmap, step_dist/8 (BASELINE configs[2])"),
+    "bands8k": dict(log2n=15, W=7680, H=4320, projection=1, step_dist=0.05, frames=240, mode="bands",
+                    desc="perspective 7680x4320 single frames over a 32768^2 fBm heightmap, interleaved 4-row tile bands "
+                         "over the GPUs, RGBA8 bands gathered to rank 0 over NCCL (BASELINE configs[4])"),
     "smoke": dict(log2n=10, W=640, H=360, projection=1, step_dist=0.05, frames=240,
                   desc="small debugging workload"),
 }
@@ -133,7 +136,8 @@ def run_cpu_reference(wl: dict, frame_ids: list[int], warmup: int, workdir: Path
     gen_s = time.perf_counter() - t0
     sample = f"{len(frame_ids)} frames of the workload's camera path at {W}x{H} (every {REF_SAMPLE_DIV}th ray per axis)"
 
-    if O.REF_BIN_O2.exists() and O.REF_BIN.exists():
+    # the reference cannot load a 32768^2 map at all (stb_image caps, int indices: SURVEY.md D-9): port only
+    if O.REF_BIN_O2.exists() and O.REF_BIN.exists() and wl["log2n"] < 15:
         hp, cp = workdir / "height.pgm", workdir / "color.tga"
         with open(hp, "wb") as f:
             f.write(b"P5\n%d %d\n255\n" % (hm.shape[1], hm.shape[0]))
@@ -232,7 +236,15 @@ def ours_arm(args, wl) -> None:
         return r.frame(projection=wl["projection"], screen_width=w, screen_height=h, cam_pos=c["pos"],
                        hang=hmrm.deg2rad(c["hang_deg"]), vang=hmrm.deg2rad(c["vang_deg"]),
                        hfov=hmrm.deg2rad(c["hfov_deg"]), ortho_width=c["ortho_width"], grid_width=GRID_WIDTH,
-                       step_dist=wl["step_dist"], traversal=traversal, flags=flags)
+                       step_dist=wl["step_dist"], traversal=traversal, flags=flags,
+                       band_count=world if (bands and w == W) else 0, band_index=rank if (bands and w == W) else 0)
+
+    def render_step(n: int, flags: int = 0):
+        """One step of the workload on this rank: a whole frame, or this rank's bands + the gather to rank 0."""
+        r.render_device(frame_of(n, flags=flags), d_out, stream.cuda_stream)
+        if bands and world > 1:
+            return MG.gather_interleaved_bands(d_out, H, rank, world)
+        return d_out
 
     def barrier():
         torch.cuda.synchronize()
@@ -240,9 +252,17 @@ def ours_arm(args, wl) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    my_frames = [(s * world + rank) % wl["frames"] for s in range(args.steps)]
-    warm_frames = [((args.steps + s) * world + rank) % wl["frames"] for s in range(args.warmup)]
-    d_out = torch.empty((H, W, 4), dtype=torch.uint8, device=f"cuda:{local}")
+    bands = wl.get("mode") == "bands"
+    if bands:
+        # every rank works on the SAME frame: its interleaved tile rows; rank 0 ends up with the whole frame
+        my_frames = [s % wl["frames"] for s in range(args.steps)]
+        warm_frames = [(args.steps + s) % wl["frames"] for s in range(args.warmup)]
+    else:
+        my_frames = [(s * world + rank) % wl["frames"] for s in range(args.steps)]
+        warm_frames = [((args.steps + s) * world + rank) % wl["frames"] for s in range(args.warmup)]
+    from heightmap_ray_marcher_b200 import multi_gpu as MG
+
+    d_out = torch.zeros((MG.padded_height(H), W, 4), dtype=torch.uint8, device=f"cuda:{local}")
     h_out = binding.pinned_empty((H, W, 4))
     stream = torch.cuda.Stream(device=local)       # a real (non-default) stream: kernels and events share it
     torch.cuda.set_stream(stream)
@@ -250,7 +270,7 @@ def ours_arm(args, wl) -> None:
     # ---- untimed statistics pass over the timed frames: reference-equivalent steps S, hits, fetches ----
     S = hits = fetches = 0
     for n in my_frames:
-        r.render_device(frame_of(n, flags=hmrm.FLAG_STATS), d_out, stream.cuda_stream)
+        render_step(n, flags=hmrm.FLAG_STATS)
         st = r.stats()
         S += st.steps
         hits += st.surf_hits
@@ -260,7 +280,7 @@ def ours_arm(args, wl) -> None:
 
     # ---- value: K frames, device-resident, CUDA events on the launching stream ----
     for n in warm_frames:
-        r.render_device(frame_of(n), d_out, stream.cuda_stream)
+        render_step(n)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -273,6 +293,8 @@ def ours_arm(args, wl) -> None:
             for n in my_frames:
                 r.render_device(frame_of(n), d_out, stream.cuda_stream)
             stream.synchronize()
+            if dist is not None:
+                break       # collectives must stay in lock step across ranks: one pass only
 
     t_wall0 = time.perf_counter()
     keep_busy(0.5)
@@ -280,19 +302,30 @@ def ours_arm(args, wl) -> None:
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for n in my_frames:
-        r.render_device(frame_of(n), d_out, stream.cuda_stream)
+        render_step(n)
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     keep_busy(0.4)
 
     # ---- e2e: the user's call — host output buffer, D2H inside the timed region ----
+    h_out_t = torch.from_numpy(h_out)          # same pinned memory, as a tensor (for the gathered frame)
+
+    def e2e_step(n: int) -> None:
+        if bands and world > 1:
+            full = render_step(n)              # bands + NCCL gather; rank 0 then reads the frame back
+            if rank == 0:
+                h_out_t.copy_(full, non_blocking=True)
+            stream.synchronize()
+        else:
+            r.render(frame_of(n), out=h_out)
+
     for n in warm_frames:
-        r.render(frame_of(n), out=h_out)
+        e2e_step(n)
     barrier()
     t0 = time.perf_counter()
     for n in my_frames:
-        r.render(frame_of(n), out=h_out)
+        e2e_step(n)
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
@@ -320,7 +353,8 @@ def ours_arm(args, wl) -> None:
         k_ms_total = sum(kernel_ms)
 
     if rank == 0:
-        rays_total = W * H * args.steps * world
+        # frames: every rank renders its own frames (weak); bands: all ranks share each frame (strong)
+        rays_total = W * H * args.steps * (1 if bands else world)
         value = rays_total / (dev_ms * 1e-3) / 1e6
         e2e_value = rays_total / (e2e_ms * 1e-3) / 1e6
         # algorithmic bytes: 8 B per reference step + 4 B colormap per hit + 4 B store per pixel
@@ -341,14 +375,19 @@ def ours_arm(args, wl) -> None:
             pass
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if bands else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "desc": wl["desc"], "traversal": args.traversal,
-                       "precision": "fp64_exact", "sharding": f"frames round-robin over {world} GPU(s), maps replicated",
+                       "precision": "fp64_exact",
+                       "sharding": (f"each frame split into interleaved 4-row tile bands over {world} GPU(s), RGBA8 bands "
+                                    "gathered to rank 0 (NCCL), maps replicated") if bands else
+                                   f"frames round-robin over {world} GPU(s), maps replicated, no collective",
                        "l2": "inputs larger than L2 (2 GiB FP64 height plane + 1 GiB RGBA8 colormap per GPU; "
                              "the camera moves every frame)" if wl["log2n"] >= 13 else "inputs may fit L2; camera moves every frame"},
-            "march_steps_per_s": S / (dev_ms * 1e-3), "ref_steps_per_frame": S / (args.steps * world),
-            "fetches_per_frame": fetches / (args.steps * world),
+            "march_steps_per_s": S / (dev_ms * 1e-3),
+            "ref_steps_per_frame": S / (args.steps * (1 if bands else world)),
+            "fetches_per_frame": fetches / (args.steps * (1 if bands else world)),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak,
                          "peak_source": "measured" if "hbm_gbs" in peaks else "fallback", "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "kernel": "k2_render", "kernel_ms": k_ms,

@@ -50,6 +50,8 @@ class Frame(C.Structure):
         ("row_end", C.c_int32),
         ("traversal", C.c_int32),
         ("flags", C.c_uint32),
+        ("band_count", C.c_int32),
+        ("band_index", C.c_int32),
     ]
 
 

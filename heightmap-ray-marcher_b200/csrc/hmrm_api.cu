@@ -237,6 +237,8 @@ int validate_frame(hmrm_ctx *c, const hmrm_frame *f, int *row_begin, int *row_en
 	if (rb == 0 && re == 0) re = f->screen_height;
 	if (rb < 0 || re > f->screen_height || rb >= re)
 		return fail(c, HMRM_ERR_INVALID, "row band [%d,%d) outside the frame", rb, re);
+	if (f->band_count < 0 || (f->band_count > 1 && (f->band_index < 0 || f->band_index >= f->band_count)))
+		return fail(c, HMRM_ERR_INVALID, "need 0 <= band_index < band_count");
 	*row_begin = rb;
 	*row_end = re;
 	return HMRM_OK;
@@ -263,7 +265,18 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	P.cycle = f->cycle;
 	P.period = f->cycle_period;
 	P.tiles_x = (W + 7) / 8;
-	P.tiles_y = (row_end - row_begin + 3) / 4;
+	const int tile_rows = (row_end - row_begin + 3) / 4;
+	if (f->band_count > 1) {
+		// interleaved bands: sky rows are almost free and terrain rows are not, so contiguous bands balance badly
+		P.tile_y_first = f->band_index;
+		P.tile_y_step = f->band_count;
+		P.tiles_y = tile_rows > f->band_index ? (tile_rows - f->band_index + f->band_count - 1) / f->band_count : 0;
+	}
+	else {
+		P.tile_y_first = 0;
+		P.tile_y_step = 1;
+		P.tiles_y = tile_rows;
+	}
 	P.map_w = c->map_w;
 	P.map_h = c->map_h;
 	const Vec3 *src[5] = {&pc.cam, &pc.ul, &pc.pr, &pc.pd, &pc.look};

@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256, 4) k2_render_skip(const __grid_constant__
 		const int ty = (int)(tile / (unsigned)P.tiles_x);
 		const int tx = (int)(tile - (unsigned)ty * (unsigned)P.tiles_x);
 		const int px = tx * 8 + (lane & 7);
-		const int py = P.row_begin + ty * 4 + (lane >> 3);
+		const int py = P.row_begin + (P.tile_y_first + ty * P.tile_y_step) * 4 + (lane >> 3);
 		const bool active = pixel_selected(P, px, py);
 
 		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u, {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};

@@ -25,7 +25,8 @@ struct RenderParams {
 	int W, H;
 	int row_begin, row_end;
 	int cycle, period;
-	int tiles_x, tiles_y;          // 8x4-pixel tiles covering rows [row_begin,row_end)
+	int tiles_x, tiles_y;          // 8x4-pixel tiles this launch renders
+	int tile_y_first, tile_y_step; // launch tile row t is frame tile row tile_y_first + t * tile_y_step (row interleave)
 	// map
 	int map_w, map_h;
 	// image plane (host-built, frame_setup.h)

@@ -72,6 +72,8 @@ typedef struct hmrm_frame {
 	int32_t row_end;        /* 0,0 = all rows */
 	int32_t traversal;      /* HMRM_TRAVERSAL_* */
 	uint32_t flags;         /* HMRM_FLAG_* */
+	int32_t band_count;     /* > 1: the 4-row tile rows of [row_begin,row_end) are dealt round-robin to band_count */
+	int32_t band_index;     /*      renderers and this call renders those with (tile_row % band_count) == band_index */
 } hmrm_frame;
 
 typedef struct hmrm_stats {

@@ -43,7 +43,7 @@ def test_abi_version_and_struct_sizes(hmrm):
     assert tuple(f.cam_pos) == (-5.0, 5.0, 0.0)                                   # :75
     assert (f.grid_width, f.step_dist, f.ortho_width) == (0.05, 0.25, 0.1)        # :65,68,98
     assert (f.cycle, f.cycle_period, f.traversal, f.flags) == (0, 1, 0, 0)
-    assert C.sizeof(hmrm.Frame) == 120 and C.sizeof(hmrm.Stats) == 64
+    assert C.sizeof(hmrm.Frame) == 128 and C.sizeof(hmrm.Stats) == 64
 
 
 def test_no_cpu_fallback_without_device(hmrm):

@@ -196,3 +196,33 @@ def test_large_frame_properties(hmrm, renderer, oracle, log2n, proj, res):
     ofb, osteps, _ = oracle.render(of, heights, cm, rows=rows)
     assert np.array_equal(a[rows[0]:rows[1]], ofb[rows[0]:rows[1]])
     assert np.array_equal(ia[rows[0]:rows[1]], osteps[rows[0]:rows[1]])
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_interleaved_bands_compose_full_frame(hmrm, renderer, oracle, world):
+    """Single-frame multi-GPU partition (BASELINE configs[4]) emulated on one GPU: every 'rank' renders its
+    interleaved tile rows into its own buffer; packing + unpacking as the gather does gives the 1-GPU frame."""
+    import torch
+
+    from heightmap_ray_marcher_b200 import multi_gpu as MG
+
+    scene = dict(S.SCENE_BY_NAME["persp_graze"], height=226)      # not a multiple of 4 * world
+    maps = H.load_scene_maps(scene, oracle)
+    H.configure(renderer, scene, maps)
+    full = renderer.render(H.product_frame(hmrm, renderer, scene)).copy()
+    Hh, W = scene["height"], scene["width"]
+    T = MG.tile_rows(Hh)
+    out = torch.zeros((T, 4, W, 4), dtype=torch.uint8, device="cuda:0")
+    for r in range(world):
+        local = torch.zeros((MG.padded_height(Hh), W, 4), dtype=torch.uint8, device="cuda:0")
+        renderer.render_device(H.product_frame(hmrm, renderer, scene, band_count=world, band_index=r), local)
+        renderer.wait()
+        packed = MG.pack_owned(local, Hh, r, world)
+        n = len(MG.owned_tile_rows(Hh, r, world))
+        out[r::world] = packed[:n]
+        # rows of other ranks were not touched
+        mask = np.ones(MG.padded_height(Hh), dtype=bool)
+        mask[MG.owned_pixel_rows(Hh, r, world)] = False
+        assert not local.cpu().numpy()[mask].any()
+    got = out.view(T * 4, W, 4)[:Hh].cpu().numpy()
+    assert np.array_equal(got, full)
