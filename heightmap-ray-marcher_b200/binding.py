@@ -89,6 +89,7 @@ PROTOTYPES = {
     "hmrm_render_device": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p, C.c_void_p]),
     "hmrm_render_async": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p]),
     "hmrm_wait": (C.c_int, [C.c_void_p]),
+    "hmrm_wait_pending": (C.c_int, [C.c_void_p, C.c_int]),
     "hmrm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "hmrm_get_step_index": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hmrm_get_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
@@ -285,6 +286,10 @@ class Renderer:
 
     def wait(self) -> None:
         self._check(self._lib.hmrm_wait(self._h))
+
+    def wait_pending(self, max_pending: int) -> None:
+        """Streaming: return once at most `max_pending` (0 or 1) frames of render_async are still in flight."""
+        self._check(self._lib.hmrm_wait_pending(self._h, max_pending))
 
     def render_device(self, frame: Frame, d_out, stream=None) -> None:
         self._check(self._lib.hmrm_render_device(self._h, C.byref(frame), _ptr(d_out), _ptr(stream)))

@@ -71,8 +71,13 @@ struct hmrm_ctx {
 	int staging_next;
 
 	// outputs
-	uint32_t *d_fb;
+	uint32_t *d_fb;              // the persistent framebuffer (the reference's framebuf, main/hmap.cpp:612)
+	uint32_t *d_fb_alt;          // second buffer so that frame n+1 can render while frame n is copied out
 	int fb_w, fb_h;
+	cudaStream_t copy_stream;
+	cudaEvent_t ev_rendered[2], ev_copied[2];
+	bool copy_pending[2];
+	int slot;                    // buffer of the most recent hmrm_render_async
 	int32_t *d_step_index;
 	size_t step_index_cap;
 	DeviceStats *d_stats;
@@ -201,11 +206,17 @@ int ensure_tables(hmrm_ctx *c, int W, int H) {
 int ensure_framebuffer(hmrm_ctx *c, int W, int H) {
 	if (c->d_fb && c->fb_w == W && c->fb_h == H) return HMRM_OK;
 	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	c->copy_pending[0] = c->copy_pending[1] = false;
 	cudaFree(c->d_fb);
-	c->d_fb = NULL;
+	cudaFree(c->d_fb_alt);
+	c->d_fb = c->d_fb_alt = NULL;
 	HMRM_CUDA(c, cudaMalloc(&c->d_fb, (size_t)W * (size_t)H * 4));
+	HMRM_CUDA(c, cudaMalloc(&c->d_fb_alt, (size_t)W * (size_t)H * 4));
 	// the reference's framebuf starts uninitialised (main/hmap.cpp:612); start from zeros instead
 	HMRM_CUDA(c, cudaMemset(c->d_fb, 0, (size_t)W * (size_t)H * 4));
+	HMRM_CUDA(c, cudaMemset(c->d_fb_alt, 0, (size_t)W * (size_t)H * 4));
+	c->slot = 0;
 	c->fb_w = W;
 	c->fb_h = H;
 	return HMRM_OK;
@@ -475,8 +486,12 @@ int hmrm_create(int device, hmrm_ctx **out) {
 		c->staging[i].consumed = NULL;
 	}
 	c->staging_next = 0;
-	c->d_fb = NULL;
+	c->d_fb = c->d_fb_alt = NULL;
 	c->fb_w = c->fb_h = 0;
+	c->copy_stream = NULL;
+	c->copy_pending[0] = c->copy_pending[1] = false;
+	c->ev_rendered[0] = c->ev_rendered[1] = c->ev_copied[0] = c->ev_copied[1] = NULL;
+	c->slot = 0;
 	c->d_step_index = NULL;
 	c->step_index_cap = 0;
 	c->d_stats = NULL;
@@ -486,6 +501,11 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->last_stream = NULL;
 
 	cudaError_t err = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+	if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
+	for (int i = 0; i < 2 && err == cudaSuccess; ++i) {
+		err = cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming);
+		if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+	}
 	if (err == cudaSuccess) err = cudaEventCreate(&c->ev_begin);
 	if (err == cudaSuccess) err = cudaEventCreate(&c->ev_end);
 	for (int i = 0; i < 2 && err == cudaSuccess; ++i)
@@ -515,7 +535,14 @@ void hmrm_destroy(hmrm_ctx *c) {
 		if (c->staging[i].host) cudaFreeHost(c->staging[i].host);
 		if (c->staging[i].consumed) cudaEventDestroy(c->staging[i].consumed);
 	}
+	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	cudaFree(c->d_fb);
+	cudaFree(c->d_fb_alt);
+	for (int i = 0; i < 2; ++i) {
+		if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]);
+		if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+	}
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	cudaFree(c->d_step_index);
 	cudaFree(c->d_stats);
 	cudaFree(c->d_tile_counter);
@@ -686,22 +713,50 @@ int hmrm_render_async(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
 	HMRM_CUDA(c, cudaSetDevice(c->device));
 	int rc = ensure_framebuffer(c, f->screen_width, f->screen_height);
 	if (rc) return rc;
-	rc = enqueue_render(c, f, c->d_fb, c->stream, true);
+	// Whole frames (cycle_period 1) alternate between two device buffers so that the copy-out of frame n overlaps
+	// the kernel of frame n+1; the progressive interleave (cycle_period > 1) accumulates in the one persistent buffer.
+	const int slot = (f->cycle_period == 1) ? (c->slot ^ 1) : 0;
+	uint32_t *fb = slot ? c->d_fb_alt : c->d_fb;
+	if (c->copy_pending[slot]) HMRM_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+	if (f->cycle_period != 1 && c->slot == 1) {
+		// the newest picture lives in the alternate buffer: a progressive frame must land on top of it
+		HMRM_CUDA(c, cudaMemcpyAsync(c->d_fb, c->d_fb_alt, (size_t)c->fb_w * (size_t)c->fb_h * 4, cudaMemcpyDeviceToDevice,
+		                             c->stream));
+	}
+	rc = enqueue_render(c, f, fb, c->stream, true);
 	if (rc) return rc;
+	HMRM_CUDA(c, cudaEventRecord(c->ev_rendered[slot], c->stream));
 	int rb = f->row_begin, re = f->row_end;
 	if (rb == 0 && re == 0) re = f->screen_height;
 	const size_t row_bytes = (size_t)f->screen_width * 4;
-	HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + (size_t)rb * row_bytes, (const uint8_t *)c->d_fb + (size_t)rb * row_bytes,
-	                             (size_t)(re - rb) * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+	HMRM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[slot], 0));
+	HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + (size_t)rb * row_bytes, (const uint8_t *)fb + (size_t)rb * row_bytes,
+	                             (size_t)(re - rb) * row_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+	HMRM_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+	c->copy_pending[slot] = true;
+	c->slot = slot;
 	return HMRM_OK;
 }
 
-int hmrm_wait(hmrm_ctx *c) {
+int hmrm_wait_pending(hmrm_ctx *c, int max_pending) {
 	if (!c) return HMRM_ERR_INVALID;
 	HMRM_CUDA(c, cudaSetDevice(c->device));
+	if (max_pending >= 1) {
+		// let the most recent frame stay in flight; the one before it must be on the host
+		const int older = c->slot ^ 1;
+		if (c->copy_pending[older]) {
+			HMRM_CUDA(c, cudaEventSynchronize(c->ev_copied[older]));
+			c->copy_pending[older] = false;
+		}
+		return HMRM_OK;
+	}
 	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	c->copy_pending[0] = c->copy_pending[1] = false;
 	return HMRM_OK;
 }
+
+int hmrm_wait(hmrm_ctx *c) { return hmrm_wait_pending(c, 0); }
 
 int hmrm_render(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
 	int rc = hmrm_render_async(c, f, rgba_out);
