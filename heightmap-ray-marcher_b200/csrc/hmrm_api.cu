@@ -54,8 +54,9 @@ struct hmrm_ctx {
 	bool maps_set, heights_set;
 	double lum[3], min_height, max_height, max_surf, min_surf;
 	// conservative fixed-point view for the skip traversal
-	uint16_t *d_mip;             // levels 0..mip_levels-1 back to back; level 0 = Zq(surf) per cell
-	uint16_t *d_dil;             // levels 1..: 3x3-block dilation of d_mip's level (what the traversal reads)
+	uint16_t *d_mip;             // what the traversal reads, levels 0..mip_levels-1 back to back: level 0 = Zq(surf)
+	                             // per cell, level l >= 1 = 3x3-block dilation of the plain max-mip level l
+	uint16_t *d_dil;             // scratch: the plain (undilated) max-mip levels 1.., input of the dilation
 	size_t mip_offset[16];
 	int mip_w[16], mip_h[16];
 	int mip_levels;
@@ -387,10 +388,10 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		P.cell_exit_scale = e_exit ? (float)std::atof(e_exit) : 4.0f;
 		P.lstart = lmin + 2 * P.lstride <= P.ltop ? lmin + 2 * P.lstride : lmin;
 		if (P.fx_bits < 1) traversal = HMRM_TRAVERSAL_BRUTE;
-		P.q0 = c->d_mip;
+		P.lv = c->d_mip;
 		for (int l = 0; l < 16; ++l) {
-			P.mip[l] = (l < c->mip_levels) ? (l == 0 ? c->d_mip : c->d_dil + (c->mip_offset[l] - c->mip_offset[1])) : NULL;
-			P.mip_w[l] = (l < c->mip_levels) ? c->mip_w[l] : 0;
+			P.lv_desc[l].x = (l < c->mip_levels) ? (unsigned)c->mip_offset[l] : 0u;
+			P.lv_desc[l].y = (l < c->mip_levels) ? (unsigned)c->mip_w[l] : 0u;
 		}
 		if (!std::isfinite(P.fx_scale)) traversal = HMRM_TRAVERSAL_BRUTE;
 	}
@@ -404,7 +405,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 
 	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_begin, stream));
 	if (traversal == HMRM_TRAVERSAL_SKIP) {
-		if (want_stats) k2_render_skip<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		if (want_stats || want_steps) k2_render_skip<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
 		else k2_render_skip<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
 	}
 	else {
@@ -633,13 +634,12 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 	                                                    (unsigned int *)(c->d_max_bits + 2));
 	HMRM_CUDA(c, cudaGetLastError());
 	for (int l = 1; l < c->mip_levels; ++l) {
-		k1_mip_reduce<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_mip + c->mip_offset[l - 1], c->mip_w[l - 1],
-		                                                      c->mip_h[l - 1], c->d_mip + c->mip_offset[l],
-		                                                      c->mip_w[l], c->mip_h[l]);
+		uint16_t *plain = c->d_dil + (c->mip_offset[l] - c->mip_offset[1]);
+		const uint16_t *below = l == 1 ? c->d_mip : c->d_dil + (c->mip_offset[l - 1] - c->mip_offset[1]);
+		k1_mip_reduce<<<c->num_sms * 8, 256, 0, c->stream>>>(below, c->mip_w[l - 1], c->mip_h[l - 1], plain, c->mip_w[l],
+		                                                      c->mip_h[l]);
 		HMRM_CUDA(c, cudaGetLastError());
-		k1_mip_dilate<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_mip + c->mip_offset[l],
-		                                                      c->d_dil + (c->mip_offset[l] - c->mip_offset[1]),
-		                                                      c->mip_w[l], c->mip_h[l]);
+		k1_mip_dilate<<<c->num_sms * 8, 256, 0, c->stream>>>(plain, c->d_mip + c->mip_offset[l], c->mip_w[l], c->mip_h[l]);
 		HMRM_CUDA(c, cudaGetLastError());
 	}
 	HMRM_CUDA(c, cudaMemcpyAsync(bits, c->d_max_bits + 2, 8, cudaMemcpyDeviceToHost, c->stream));

@@ -92,12 +92,22 @@ __device__ __forceinline__ bool fixed_axis(double t, unsigned mask, int &v) {
 	return __double2hiint(t) == 0x43380000 && v >= 0 && (((unsigned)v + 1u) & mask) > 1u;
 }
 
+// A sample in the fixed-point view.  vx >> k and vy >> k ARE the reference's cell indices (exact): when the
+// fixed-point value is too close to a cell edge, negative, huge or NaN, the reference's own divide decides and
+// the coordinate is replaced by the centre of that cell (or by an out-of-grid marker); `fast` then is false and
+// the sample may not be the end point of a jump.
 struct MarchPos {
-	int vx, vy;     // fixed-point cell coordinates (estimates when !fast)
-	int cx, cy;     // the reference's cell indices (exact), possibly outside the grid
+	int vx, vy;
 	int zq;         // Zq(z)
-	bool fast;      // vx, vy decoded exactly and unambiguously
+	bool fast;
 };
+
+__device__ __forceinline__ int exact_axis(double c, double gw, int dim, int k) {
+	const int cell = trunc_cell(fdiv(c, gw));                 // the reference's expression, main/hmap.cpp:1001-1004
+	if (cell < 0) return -1;
+	if (cell >= dim) return INT_MAX;
+	return (cell << k) + (1 << (k - 1));
+}
 
 __device__ __forceinline__ MarchPos locate(const RenderParams &P, double x, double y, double z) {
 	MarchPos r;
@@ -106,28 +116,19 @@ __device__ __forceinline__ MarchPos locate(const RenderParams &P, double x, doub
 	const bool okx = fixed_axis(__fma_rn(x, P.fx_scale, HMRM_MAGIC), mask, r.vx);
 	const bool oky = fixed_axis(__fma_rn(y, -P.fx_scale, HMRM_MAGIC), mask, r.vy);
 	r.fast = okx && oky;
-	r.cx = r.vx >> k;
-	r.cy = r.vy >> k;
 	if (!r.fast) {
-		// near a cell edge, negative, huge or NaN: evaluate the reference's own expression
-		if (!okx) {
-			r.cx = trunc_cell(fdiv(x, P.gw));
-			r.vx = (r.cx >= 0 && r.cx < P.map_w) ? (r.cx << k) + (1 << (k - 1)) : 0;
-		}
-		if (!oky) {
-			r.cy = trunc_cell(fdiv(-y, P.gw));
-			r.vy = (r.cy >= 0 && r.cy < P.map_h) ? (r.cy << k) + (1 << (k - 1)) : 0;
-		}
+		if (!okx) r.vx = exact_axis(x, P.gw, P.map_w, k);
+		if (!oky) r.vy = exact_axis(-y, P.gw, P.map_h, k);
 	}
 	r.zq = zq_of(z, P.zq_scale, P.zq_offset);
 	return r;
 }
 
-// Per-level view of "how far can this sample go": block bounds in fixed point and step estimates.
-struct LevelEst {
-	int lo_x, hi_x, lo_y, hi_y;   // block extent (clipped to the grid) in fixed-point units
-	float est_xy, est_z;          // steps until the block edge / until Zq(z) could reach q (estimates)
-};
+__device__ __forceinline__ float fast_rcp(float x) {
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
 
 template <bool kStats>
 __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray, double ex, double ey, double ez,
@@ -144,77 +145,80 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 	ax.S = ay.S = az.S = 0.0;
 
 	// per-step motion in fixed-point units: estimates only, they never decide a result
-	const float dxf = (float)(ax.s * P.fx_scale);
-	const float dyf = (float)(-ay.s * P.fx_scale);
-	const float dzf = (float)(az.s * P.zq_scale);
-	const float inv_adx = 1.0f / fabsf(dxf), inv_ady = 1.0f / fabsf(dyf), inv_adz = 1.0f / fabsf(dzf);
-	const int cell_exit = (int)fminf(P.cell_exit_scale * fabsf(dzf) + 32.0f, 1.0e9f);
-	const int grid_vx = P.map_w << k, grid_vy = P.map_h << k;   // <= 2^30
+	const float adx = fabsf((float)(ax.s * P.fx_scale)), ady = fabsf((float)(ay.s * P.fx_scale));
+	const float adz = fabsf((float)(az.s * P.zq_scale));
+	const float inv_adx = fast_rcp(adx), inv_ady = fast_rcp(ady), inv_adz = fast_rcp(adz);
+	const bool x_up = __double2hiint(ax.s) >= 0;       // vx grows with x
+	const bool y_up = __double2hiint(ay.s) < 0;        // vy grows with -y
+	const bool z_down = az.s < 0.0;
+	const int cell_exit = (int)fminf(P.cell_exit_scale * adz + 32.0f, 1.0e9f);
+	const unsigned grid_vx = (unsigned)P.map_w << k, grid_vy = (unsigned)P.map_h << k;   // <= 2^30
 
-	auto probe = [&](int level, int cx, int cy) -> int {
-		return (int)__ldg(P.mip[level] + (size_t)(cy >> level) * (size_t)P.mip_w[level] + (size_t)(cx >> level));
+	// one level of the pyramid: lv_desc[l] = (element offset, pitch); level 0 is Zq(surf) per cell, levels >= 1
+	// hold the maximum over the 2^l-cell block and its eight neighbours
+	auto probe = [&](int level, int vx, int vy) -> int {
+		const uint2 d = P.lv_desc[level];
+		const unsigned idx = d.x + (unsigned)(vy >> (k + level)) * d.y + (unsigned)(vx >> (k + level));
+		return (int)__ldg(P.lv + idx);
 	};
-	auto estimate = [&](int level, const MarchPos &c, int q) -> LevelEst {
-		LevelEst e;
-		const int shift = k + level;
-		const int bx = c.cx >> level, by = c.cy >> level;
-		// levels >= 1 hold the 3x3-dilated maximum: the cleared region is the block and its eight neighbours
-		e.lo_x = max(bx - 1, 0) << shift;
-		e.lo_y = max(by - 1, 0) << shift;
-		e.hi_x = (int)min((unsigned)(bx + 2) << shift, (unsigned)grid_vx);
-		e.hi_y = (int)min((unsigned)(by + 2) << shift, (unsigned)grid_vy);
-		const int edge_x = (dxf > 0.0f) ? (e.hi_x - c.vx) : (c.vx - e.lo_x);
-		const int edge_y = (dyf > 0.0f) ? (e.hi_y - c.vy) : (c.vy - e.lo_y);
-		e.est_xy = fminf(__int2float_rz(edge_x) * inv_adx, __int2float_rz(edge_y) * inv_ady);
-		e.est_z = (dzf < 0.0f) ? __int2float_rz(c.zq - q) * inv_adz : 3.0e38f;
-		return e;
+	// extent (clipped to the grid) of the neighbourhood a level-`level` texel covers, in fixed-point units
+	auto extent = [&](int level, int v, unsigned grid, int &lo, int &hi) {
+		const int sh = k + level;
+		const int b = v >> sh;
+		lo = max(b - 1, 0) << sh;
+		hi = (int)min((unsigned)(b + 2) << sh, grid);
 	};
 
 	unsigned steps = 0u, fetches = 0u;
 	int level = P.lstart;
 	MarchPos cur = locate(P, ax.p, ay.p, az.p);
 
-	while ((unsigned)cur.cx < (unsigned)P.map_w && (unsigned)cur.cy < (unsigned)P.map_h) {   // :1006-1011
-		// ---- A: find a level whose block this sample clears (descend), or reach the cell itself ----
-		int q = probe(level, cur.cx, cur.cy);
+	while ((unsigned)cur.vx < grid_vx && (unsigned)cur.vy < grid_vy) {       // :1006-1011
+		// ---- A: find a level whose neighbourhood this sample clears (descend), or reach the cell itself ----
+		int q = probe(level, cur.vx, cur.vy);
 		if (kStats) fetches += 1u;
 		while (cur.zq <= q && level > 0) {
 			level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
-			q = probe(level, cur.cx, cur.cy);
+			q = probe(level, cur.vx, cur.vy);
 			if (kStats) { fetches += 1u; tally.dbg[3] += 1u; }
 		}
 
 		int m = 1;
-		int next_level = level;
-		LevelEst e;
-		e.lo_x = e.lo_y = e.hi_x = e.hi_y = 0;
+		int jl = level;          // level whose neighbourhood bounds this advance
 		if (cur.zq > q) {
-			// above every surface value of the block: the sample cannot hit
+			// above every surface value of the neighbourhood: the sample cannot hit
 			if (level > 0) {
-				e = estimate(level, cur, q);
-				// climb while z leaves room for (much) wider blocks and the wider block is cleared too
-				while (e.est_z >= 4.0f * e.est_xy && level + P.lstride <= P.ltop) {
-					const int q2 = probe(level + P.lstride, cur.cx, cur.cy);
+				float est_xy, est_z;
+				for (;;) {
+					int lo, hi;
+					extent(level, cur.vx, grid_vx, lo, hi);
+					const float ex_ = __int2float_rz(x_up ? hi - cur.vx : cur.vx - lo) * inv_adx;
+					extent(level, cur.vy, grid_vy, lo, hi);
+					const float ey_ = __int2float_rz(y_up ? hi - cur.vy : cur.vy - lo) * inv_ady;
+					est_xy = fminf(ex_, ey_);
+					est_z = z_down ? __int2float_rz(cur.zq - q) * inv_adz : 3.0e38f;
+					// climb while z leaves room for (much) wider blocks and the wider neighbourhood is cleared too
+					if (!(est_z >= 4.0f * est_xy) || level + P.lstride > P.ltop) break;
+					const int q2 = probe(level + P.lstride, cur.vx, cur.vy);
 					if (kStats) fetches += 1u;
 					if (cur.zq <= q2) break;
 					level += P.lstride;
 					q = q2;
-					e = estimate(level, cur, q);
 				}
-				const float est = fminf(fminf(e.est_xy, e.est_z), (float)HMRM_JUMP_CAP) * 0.999f;
+				jl = level;
+				const float est = fminf(fminf(est_xy, est_z), (float)HMRM_JUMP_CAP) * 0.999f;
 				m = (est >= 2.0f) ? __float2int_rz(est) : 1;
-				next_level = level;
-				// a z-limited jump ends just above q: the next sample will need a finer block
-				if (e.est_z < e.est_xy) next_level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
+				// a z-limited jump ends just above q: the next sample will need a finer level
+				if (est_z < est_xy) level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
 			}
 			else {
 				if (kStats) tally.dbg[4] += 1u;
-				if (cur.zq - q > cell_exit) next_level = P.lmin;
+				if (cur.zq - q > cell_exit) level = P.lmin;
 			}
 		}
 		else {
 			// level 0 and not above: the reference's own test on this cell (main/hmap.cpp:1013-1016)
-			const size_t cell = (size_t)cur.cx + (size_t)cur.cy * (size_t)P.map_w;
+			const size_t cell = (size_t)(cur.vx >> k) + (size_t)(cur.vy >> k) * (size_t)P.map_w;
 			bool hit = cur.zq < q;
 			if (kStats) tally.dbg[5] += 1u;
 			if (!hit) {
@@ -224,13 +228,13 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 			if (hit) {
 				rgba = hit_colour(P, __ldg(P.color + cell));
 				real_hit = true;
-				first_hit = (steps > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)steps;
+				if (kStats) first_hit = (steps > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)steps;
 				steps += 1u;
 				break;
 			}
 		}
 
-		// ---- C: advance m samples: closed form when m >= 2, the reference's plain add when m == 1 ----
+		// ---- C: advance m samples: closed form when m >= 2 (end point verified), the reference's plain add otherwise ----
 		bool jump = false;
 		double md = 1.0;
 		if (m >= 2) {
@@ -248,10 +252,13 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 		double nz = jump ? __fma_rn(md, az.S, az.p) : fadd(az.p, az.s);
 		MarchPos nxt = locate(P, nx, ny, nz);
 		if (jump) {
-			// (1) same binades, (3) end point in the same block (one unit clear of its edges), in the grid, above q
-			bool in_binade = binade_tag(nx) == ax.tag && binade_tag(ny) == ay.tag && binade_tag(nz) == az.tag;
-			bool ok = in_binade && nxt.fast && nxt.vx - e.lo_x >= 1 && e.hi_x - nxt.vx >= 2 && nxt.vy - e.lo_y >= 1 &&
-			          e.hi_y - nxt.vy >= 2 && nxt.zq > q;
+			// (1) same binades, (3) end point inside the cleared neighbourhood (one unit clear of its edges), above q
+			int lo_x, hi_x, lo_y, hi_y;
+			extent(jl, cur.vx, grid_vx, lo_x, hi_x);
+			extent(jl, cur.vy, grid_vy, lo_y, hi_y);
+			const bool in_binade = binade_tag(nx) == ax.tag && binade_tag(ny) == ay.tag && binade_tag(nz) == az.tag;
+			bool ok = in_binade && nxt.fast && nxt.vx - lo_x >= 1 && hi_x - nxt.vx >= 2 && nxt.vy - lo_y >= 1 &&
+			          hi_y - nxt.vy >= 2 && nxt.zq > q;
 			if (!in_binade) {
 				// some axis would leave its binade: go exactly as far as the binade allows, the next plain step crosses
 				int m2 = m;
@@ -266,9 +273,8 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 					nz = __fma_rn(md, az.S, az.p);
 					nxt = locate(P, nx, ny, nz);
 					ok = binade_tag(nx) == ax.tag && binade_tag(ny) == ay.tag && binade_tag(nz) == az.tag && nxt.fast &&
-					     nxt.vx - e.lo_x >= 1 && e.hi_x - nxt.vx >= 2 && nxt.vy - e.lo_y >= 1 && e.hi_y - nxt.vy >= 2 &&
-					     nxt.zq > q;
-					next_level = level;
+					     nxt.vx - lo_x >= 1 && hi_x - nxt.vx >= 2 && nxt.vy - lo_y >= 1 && hi_y - nxt.vy >= 2 && nxt.zq > q;
+					level = jl;
 				}
 			}
 			if (!ok) {
@@ -278,7 +284,7 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 				ny = fadd(ay.p, ay.s);
 				nz = fadd(az.p, az.s);
 				nxt = locate(P, nx, ny, nz);
-				next_level = level;
+				level = jl;
 			}
 		}
 		if (!jump) {
@@ -292,13 +298,12 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 		}
 		if (kStats) {
 			if (jump) { tally.dbg[0] += 1u; tally.dbg[1] += (unsigned)m; }
-			else if (level > 0) tally.dbg[2] += 1u;
+			else if (jl > 0) tally.dbg[2] += 1u;
 			if (!nxt.fast) tally.dbg[7] += 1u;
 		}
 		ax.p = nx; ay.p = ny; az.p = nz;
 		cur = nxt;
 		steps += (unsigned)m;
-		level = next_level;
 	}
 	tally.steps = steps;
 	tally.fetches = fetches;

@@ -4,6 +4,7 @@
 #define HMRM_RENDER_PARAMS_H
 
 #include <stdint.h>
+#include <vector_types.h>
 
 namespace hmrm {
 
@@ -55,9 +56,9 @@ struct RenderParams {
 	int lmin, lstride, ltop;       // mip levels used this frame: lmin, lmin+lstride, ... <= ltop (0 = cell test)
 	int lstart;                    // level of a ray's first test
 	float cell_exit_scale;         // leave cell-by-cell mode when Zq(z) - q exceeds this many steps of descent
-	const uint16_t *q0;            // Zq(surf) per cell, row-major [map_h][map_w]
-	const uint16_t *mip[16];       // mip[l]: max of q0 over 2^l x 2^l blocks, row-major, pitch mip_w[l]; mip[0] == q0
-	int mip_w[16];
+	const uint16_t *lv;            // all levels back to back: level 0 = Zq(surf) per cell (row-major [map_h][map_w]),
+	                               // level l >= 1 = max of level 0 over the 2^l x 2^l block and its eight neighbours
+	uint2 lv_desc[16];             // per level: (element offset into lv, row pitch)
 	uint32_t bg_rgba;              // bg colour with alpha 255
 	uint8_t bg[3];
 	uint8_t pad;

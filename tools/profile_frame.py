@@ -16,6 +16,7 @@ ap.add_argument("--traversal", default="skip")
 ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--first", type=int, default=0)
 ap.add_argument("--stats", action="store_true")
+ap.add_argument("--vang", type=float, default=None, help="override vang (degrees), e.g. 30 = all sky")
 args = ap.parse_args()
 
 hmrm = hmrm_pkg.load()
@@ -26,6 +27,8 @@ r.synth_maps(wl["log2n"], bench.SEED)
 trav = {"auto": 0, "brute": 1, "skip": 2}[args.traversal]
 for i in range(args.frames):
     c = bench.camera(wl, args.first + i)
+    if args.vang is not None:
+        c["vang_deg"] = args.vang
     f = r.frame(projection=wl["projection"], screen_width=wl["W"], screen_height=wl["H"], cam_pos=c["pos"],
                 hang=hmrm.deg2rad(c["hang_deg"]), vang=hmrm.deg2rad(c["vang_deg"]), hfov=hmrm.deg2rad(c["hfov_deg"]),
                 ortho_width=c["ortho_width"], grid_width=bench.GRID_WIDTH, step_dist=wl["step_dist"], traversal=trav,
