@@ -616,9 +616,13 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 	q.min_height = min_height;
 	q.span = max_height - min_height;
 	const long long n = (long long)c->map_w * c->map_h;
+	// (1) range of surf from a sample of the rows (at most ~8 M cells): only the quantiser's resolution depends on it
 	const unsigned long long init_bits[3] = {0ULL, ~0ULL, 0ULL};
 	HMRM_CUDA(c, cudaMemcpyAsync(c->d_max_bits, init_bits, sizeof init_bits, cudaMemcpyHostToDevice, c->stream));
-	k1_prepass<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, n, q, c->d_surf, NULL, c->d_max_bits, c->d_max_bits + 1);
+	int row_stride = (int)((n + (8LL << 20) - 1) / (8LL << 20));
+	if (row_stride < 1) row_stride = 1;
+	k1_range<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, c->map_w, c->map_h, row_stride, q, c->d_max_bits,
+	                                                 c->d_max_bits + 1);
 	HMRM_CUDA(c, cudaGetLastError());
 	unsigned long long bits[3] = {0ULL, 0ULL, 0ULL};
 	HMRM_CUDA(c, cudaMemcpyAsync(bits, c->d_max_bits, 16, cudaMemcpyDeviceToHost, c->stream));
@@ -626,25 +630,47 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 	c->max_surf = from_ordered_bits(bits[0]);
 	c->min_surf = from_ordered_bits(bits[1]);
 
-	// Zq: surf range [min_surf, max_surf] -> [16, 65016] (16-bit, with headroom for the rounding of the constants)
+	// Zq: sampled surf range [min_surf, max_surf] -> [2000, 63000] of the 16-bit scale; values outside clamp (and tie)
+	if (const char *shrink = std::getenv("HMRM_ZQ_RANGE_SHRINK")) {
+		// test hook: pretend the sampled range was (much) too narrow, so that most values clamp and tie
+		const double f = std::atof(shrink), mid = 0.5 * (c->max_surf + c->min_surf), half = 0.5 * (c->max_surf - c->min_surf);
+		c->min_surf = mid - f * half;
+		c->max_surf = mid + f * half;
+	}
 	const double range = c->max_surf - c->min_surf;
-	c->zq_scale = (range > 0.0 && std::isfinite(range) && std::isfinite(65000.0 / range)) ? 65000.0 / range : 1.0;
-	c->zq_offset = HMRM_MAGIC + (16.0 - c->min_surf * c->zq_scale);
-	k1_quantise<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_surf, n, c->zq_scale, c->zq_offset, c->d_mip,
-	                                                    (unsigned int *)(c->d_max_bits + 2));
-	HMRM_CUDA(c, cudaGetLastError());
+	c->zq_scale = (range > 0.0 && std::isfinite(range) && std::isfinite(61000.0 / range)) ? 61000.0 / range : 1.0;
+	c->zq_offset = HMRM_MAGIC + (2000.0 - c->min_surf * c->zq_scale);
+
+	// (2) fused build of surf, level 0 and the plain max-mip levels 1, 2; (3) remaining levels; (4) 3x3 dilation
+	{
+		uint16_t *plain1 = c->mip_levels > 1 ? c->d_dil : NULL;
+		uint16_t *plain2 = c->mip_levels > 2 ? c->d_dil + (c->mip_offset[2] - c->mip_offset[1]) : NULL;
+		if (plain1) {
+			k1_build<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, c->map_w, c->map_h, q, c->zq_scale, c->zq_offset,
+			                                                 c->d_surf, c->d_mip, plain1, c->mip_w[1], plain2,
+			                                                 c->mip_levels > 2 ? c->mip_w[2] : 0);
+		}
+		else {
+			// 1x1 map: no pyramid
+			k1_prepass<<<1, 32, 0, c->stream>>>(c->d_rgb, n, q, c->d_surf, NULL, NULL, NULL);
+			k1_quantise<<<1, 32, 0, c->stream>>>(c->d_surf, n, c->zq_scale, c->zq_offset, c->d_mip,
+			                                     (unsigned int *)(c->d_max_bits + 2));
+		}
+		HMRM_CUDA(c, cudaGetLastError());
+	}
 	for (int l = 1; l < c->mip_levels; ++l) {
 		uint16_t *plain = c->d_dil + (c->mip_offset[l] - c->mip_offset[1]);
-		const uint16_t *below = l == 1 ? c->d_mip : c->d_dil + (c->mip_offset[l - 1] - c->mip_offset[1]);
-		k1_mip_reduce<<<c->num_sms * 8, 256, 0, c->stream>>>(below, c->mip_w[l - 1], c->mip_h[l - 1], plain, c->mip_w[l],
-		                                                      c->mip_h[l]);
-		HMRM_CUDA(c, cudaGetLastError());
+		if (l >= 3) {
+			const uint16_t *below = c->d_dil + (c->mip_offset[l - 1] - c->mip_offset[1]);
+			k1_mip_reduce<<<c->num_sms * 8, 256, 0, c->stream>>>(below, c->mip_w[l - 1], c->mip_h[l - 1], plain, c->mip_w[l],
+			                                                      c->mip_h[l]);
+			HMRM_CUDA(c, cudaGetLastError());
+		}
 		k1_mip_dilate<<<c->num_sms * 8, 256, 0, c->stream>>>(plain, c->d_mip + c->mip_offset[l], c->mip_w[l], c->mip_h[l]);
 		HMRM_CUDA(c, cudaGetLastError());
 	}
-	HMRM_CUDA(c, cudaMemcpyAsync(bits, c->d_max_bits + 2, 8, cudaMemcpyDeviceToHost, c->stream));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
-	c->skip_ready = (bits[0] == 0ULL) && std::isfinite(c->zq_offset);
+	c->skip_ready = std::isfinite(c->zq_offset) && std::isfinite(c->zq_scale) && c->zq_scale > 0.0;
 	c->lum[0] = lum[0];
 	c->lum[1] = lum[1];
 	c->lum[2] = lum[2];

@@ -20,8 +20,14 @@ struct PrepassParams {
 	double span;          // fl(max_height - min_height)
 };
 
+// exact u8 -> double without the quarter-rate I2F: (2^52 + n) - 2^52
+__device__ __forceinline__ double byte_to_double(uint32_t n) {
+	return fsub(__hiloint2double(0x43300000, (int)n), 4503599627370496.0);
+}
+
 __device__ __forceinline__ double height_of(const PrepassParams &q, uint32_t r, uint32_t g, uint32_t b) {
-	double v = fadd(fadd(fmul(q.lum_r, (double)r), fmul(q.lum_g, (double)g)), fmul(q.lum_b, (double)b));
+	double v = fadd(fadd(fmul(q.lum_r, byte_to_double(r)), fmul(q.lum_g, byte_to_double(g))),
+	                fmul(q.lum_b, byte_to_double(b)));
 	if (v < 0.0) v = 0.0;
 	else if (v > 255.0) v = 255.0;
 	return fadd(fmul(fdiv(v, 255.0), q.span), q.min_height);
@@ -100,18 +106,120 @@ __device__ __forceinline__ int zq_of(double z, double zq_scale, double zq_offset
 	return (t > HMRM_MAGIC) ? INT_MAX : INT_MIN;   // far above / far below every surface value (NaN: below)
 }
 
+// Zq clamped to 16 bits.  Clamping keeps Zq monotone (weakly), so the two implications above survive as long as
+// BOTH sides are clamped: values beyond the range simply tie and fall back to the FP64 comparison.  That makes any
+// choice of scale/offset safe — the range is only estimated from a sample of the map (k1_range).
+__device__ __forceinline__ int zq16(double z, double zq_scale, double zq_offset) {
+	return min(max(zq_of(z, zq_scale, zq_offset), 0), 65535);
+}
+
+// min / max of surf over every `row_stride`-th row (order-preserving bit patterns, atomics)
+__global__ void __launch_bounds__(256) k1_range(const uint8_t *__restrict__ rgb8, int w, int h, int row_stride,
+                                                PrepassParams q, unsigned long long *__restrict__ max_bits,
+                                                unsigned long long *__restrict__ min_bits) {
+	unsigned long long local_max = 0ULL, local_min = ~0ULL;
+	const int rows = (h + row_stride - 1) / row_stride;
+	const long long n = (long long)rows * w;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		const int x = (int)(i % w);
+		const long long y = (i / w) * row_stride;
+		const uint8_t *px = rgb8 + 3 * (y * w + x);
+		const unsigned long long ob = ordered_bits(fadd(height_of(q, px[0], px[1], px[2]), q.min_height));
+		if (ob > local_max) local_max = ob;
+		if (ob < local_min) local_min = ob;
+	}
+	for (int off = 16; off > 0; off >>= 1) {
+		const unsigned long long a = __shfl_xor_sync(0xFFFFFFFFu, local_max, off);
+		const unsigned long long b = __shfl_xor_sync(0xFFFFFFFFu, local_min, off);
+		if (a > local_max) local_max = a;
+		if (b < local_min) local_min = b;
+	}
+	if ((threadIdx.x & 31) == 0) {
+		if (local_max != 0ULL) atomicMax(max_bits, local_max);
+		if (local_min != ~0ULL) atomicMin(min_bits, local_min);
+	}
+}
+
+// Fused build: one thread owns a 4x4 block of cells.  Reads RGB8 once, writes surf (FP64), level 0 (Zq16 per cell)
+// and the plain max-mip levels 1 and 2 of that block.  HBM-bound: 3 B in, 8 + 2 + 0.5 + 0.125 B out per cell.
+__global__ void __launch_bounds__(256) k1_build(const uint8_t *__restrict__ rgb8, int w, int h, PrepassParams q,
+                                                double zq_scale, double zq_offset, double *__restrict__ surf,
+                                                uint16_t *__restrict__ lv0, uint16_t *__restrict__ plain1, int w1,
+                                                uint16_t *__restrict__ plain2, int w2) {
+	const int tiles_x = (w + 3) / 4, tiles_y = (h + 3) / 4;
+	const long long n_tiles = (long long)tiles_x * tiles_y;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	const bool vec = (w & 3) == 0;     // rows are 4-byte aligned in rgb8, 8-byte in lv0, 32-byte in surf
+	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += stride) {
+		const int bx = (int)(t % tiles_x), by = (int)(t / tiles_x);
+		const int x0 = bx * 4, y0 = by * 4;
+		int m1[2][2] = {{0, 0}, {0, 0}};
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int y = y0 + j;
+			if (y >= h) break;
+			const size_t row = (size_t)y * (size_t)w + (size_t)x0;
+			uint32_t r[4], g[4], b[4];
+			int valid = min(4, w - x0);
+			if (vec) {
+				const uint32_t *p = (const uint32_t *)(rgb8 + 3 * row);
+				const uint32_t a0 = __ldg(p), a1 = __ldg(p + 1), a2 = __ldg(p + 2);
+				r[0] = a0 & 255u; g[0] = (a0 >> 8) & 255u; b[0] = (a0 >> 16) & 255u;
+				r[1] = a0 >> 24; g[1] = a1 & 255u; b[1] = (a1 >> 8) & 255u;
+				r[2] = (a1 >> 16) & 255u; g[2] = a1 >> 24; b[2] = a2 & 255u;
+				r[3] = (a2 >> 8) & 255u; g[3] = (a2 >> 16) & 255u; b[3] = a2 >> 24;
+			}
+			else {
+				for (int i = 0; i < 4; ++i) {
+					const bool in = i < valid;
+					const uint8_t *p = rgb8 + 3 * (row + (in ? i : 0));
+					r[i] = p[0]; g[i] = p[1]; b[i] = p[2];
+				}
+			}
+			double s[4];
+			int zq[4];
+#pragma unroll
+			for (int i = 0; i < 4; ++i) {
+				s[i] = fadd(height_of(q, r[i], g[i], b[i]), q.min_height);
+				zq[i] = zq16(s[i], zq_scale, zq_offset);
+				if (i < valid) m1[j >> 1][i >> 1] = max(m1[j >> 1][i >> 1], zq[i]);
+			}
+			if (vec) {
+				double2 *sp = (double2 *)(surf + row);
+				sp[0] = make_double2(s[0], s[1]);
+				sp[1] = make_double2(s[2], s[3]);
+				*(uint2 *)(lv0 + row) = make_uint2((unsigned)zq[0] | ((unsigned)zq[1] << 16), (unsigned)zq[2] | ((unsigned)zq[3] << 16));
+			}
+			else {
+				for (int i = 0; i < valid; ++i) {
+					surf[row + i] = s[i];
+					lv0[row + i] = (uint16_t)zq[i];
+				}
+			}
+		}
+		// plain level 1: 2x2 texels of this block (those that exist), level 2: one texel
+		const int h1 = (h + 1) / 2;
+		int m2 = 0;
+		for (int j = 0; j < 2; ++j) {
+			for (int i = 0; i < 2; ++i) {
+				const int tx = bx * 2 + i, ty = by * 2 + j;
+				if (tx < w1 && ty < h1) plain1[(size_t)ty * w1 + tx] = (uint16_t)m1[j][i];
+				m2 = max(m2, m1[j][i]);
+			}
+		}
+		if (plain2) plain2[(size_t)by * w2 + bx] = (uint16_t)m2;
+	}
+}
+
 // q0[p] = Zq(surf[p]); flags an error if a value does not fit 16 bits (cannot happen with the host's scale)
 __global__ void __launch_bounds__(256) k1_quantise(const double *__restrict__ surf, long long n, double zq_scale,
                                                    double zq_offset, uint16_t *__restrict__ q0,
                                                    unsigned int *__restrict__ error_flag) {
 	const long long stride = (long long)gridDim.x * blockDim.x;
 	for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-		const int q = zq_of(surf[p], zq_scale, zq_offset);
-		if (q < 0 || q > 65535) {
-			atomicOr(error_flag, 1u);
-			q0[p] = 65535;
-		}
-		else q0[p] = (uint16_t)q;
+		(void)error_flag;
+		q0[p] = (uint16_t)zq16(surf[p], zq_scale, zq_offset);
 	}
 }
 
@@ -135,8 +243,33 @@ __global__ void __launch_bounds__(256) k1_mip_reduce(const uint16_t *__restrict_
 // AND the eight blocks around it, so a jump may run on into the neighbouring blocks instead of stopping at an edge.
 __global__ void __launch_bounds__(256) k1_mip_dilate(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst,
                                                      int w, int h) {
-	const long long n = (long long)w * h;
 	const long long stride = (long long)gridDim.x * blockDim.x;
+	if ((w & 3) == 0) {
+		// four outputs per thread: per input row one 8-byte load plus the two horizontal neighbours
+		const int wq = w / 4;
+		const long long nq = (long long)wq * h;
+		for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nq; t += stride) {
+			const int xq = (int)(t % wq), y = (int)(t / wq);
+			const int x = xq * 4;
+			unsigned o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+			for (int dy = -1; dy <= 1; ++dy) {
+				const int yy = y + dy;
+				if (yy < 0 || yy >= h) continue;
+				const uint16_t *row = src + (size_t)yy * w;
+				const uint2 v = __ldg((const uint2 *)(row + x));
+				const unsigned c0 = v.x & 0xFFFFu, c1 = v.x >> 16, c2 = v.y & 0xFFFFu, c3 = v.y >> 16;
+				const unsigned l = x > 0 ? (unsigned)__ldg(row + x - 1) : 0u;
+				const unsigned r = x + 4 < w ? (unsigned)__ldg(row + x + 4) : 0u;
+				o0 = max(o0, max(l, max(c0, c1)));
+				o1 = max(o1, max(c0, max(c1, c2)));
+				o2 = max(o2, max(c1, max(c2, c3)));
+				o3 = max(o3, max(c2, max(c3, r)));
+			}
+			*(uint2 *)(dst + (size_t)y * w + x) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+		}
+		return;
+	}
+	const long long n = (long long)w * h;
 	for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
 		const int x = (int)(p % w), y = (int)(p / w);
 		uint16_t m = 0;

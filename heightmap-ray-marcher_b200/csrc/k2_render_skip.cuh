@@ -120,7 +120,7 @@ __device__ __forceinline__ MarchPos locate(const RenderParams &P, double x, doub
 		if (!okx) r.vx = exact_axis(x, P.gw, P.map_w, k);
 		if (!oky) r.vy = exact_axis(-y, P.gw, P.map_h, k);
 	}
-	r.zq = zq_of(z, P.zq_scale, P.zq_offset);
+	r.zq = zq16(z, P.zq_scale, P.zq_offset);      // clamped exactly as K1 clamps the stored values
 	return r;
 }
 

@@ -166,6 +166,29 @@ def test_streaming_async_frames_equal_synchronous_frames(hmrm, renderer, oracle)
     assert np.array_equal(out[sel], want[0][sel]) and np.array_equal(out[~sel], want[-1][~sel])
 
 
+@pytest.mark.parametrize("shrink", ["0.3", "0.02", "0"])
+@pytest.mark.parametrize("name", ["persp_basic", "ortho_fine", "noise_lum_neg", "crop_ortho"])
+def test_quantiser_range_never_affects_results(hmrm, oracle, name, shrink, monkeypatch):
+    """The 16-bit height quantiser's range is only estimated from a sample of the map; values outside clamp on both
+    sides of the comparison and tie (FP64 decides).  Force a far too narrow range: frames and step indices must
+    still be bit-exact, only the number of fetches may change."""
+    monkeypatch.setenv("HMRM_ZQ_RANGE_SHRINK", shrink)
+    scene = S.SCENE_BY_NAME[name]
+    maps = H.load_scene_maps(scene, oracle)
+    r = hmrm.Renderer(0)
+    try:
+        H.configure(r, scene, maps)
+        f = H.product_frame(hmrm, r, scene, traversal=2, flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX)
+        got = r.render(f)
+        steps = r.step_index(f)
+        st = r.stats()
+    finally:
+        r.close()
+    ofb, osteps, ost = H.oracle_render_scene(oracle, scene, maps)
+    assert np.array_equal(got, ofb) and np.array_equal(steps, osteps)
+    assert (st.steps, st.surf_hits, st.box_hits) == (ost.steps, ost.surf_hits, ost.box_hits)
+
+
 def test_invalid_arguments_are_rejected(hmrm, renderer, oracle):
     scene = S.SCENE_BY_NAME["persp_basic"]
     H.configure(renderer, scene, H.load_scene_maps(scene, oracle))
