@@ -300,7 +300,7 @@ class Renderer:
         return st
 
     def debug_counters(self) -> list:
-        out = (C.c_int64 * 8)()
+        out = (C.c_int64 * 12)()
         self._check(self._lib.hmrm_get_debug_counters(self._h, out))
         return list(out)
 

@@ -7,12 +7,14 @@
 // There is no CPU rendering path in this library.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/hmrm.h"
@@ -81,6 +83,11 @@ struct hmrm_ctx {
 	int slot;                    // buffer of the most recent hmrm_render_async
 	int32_t *d_step_index;
 	size_t step_index_cap;
+	// tile-row schedule (expensive rows first), cached per view geometry
+	int *d_row_order;
+	int row_order_cap;
+	double row_key[8];
+	bool row_key_valid;
 	DeviceStats *d_stats;
 	unsigned int *d_tile_counter;
 	bool last_had_stats, last_had_step_index, timing_valid;
@@ -330,6 +337,68 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		P.cos_va = c->d_sph + 2 * W + H;
 	}
 
+	// Tile-row schedule: rows whose rays graze the terrain (direction just below the horizon) march for hundreds of
+	// steps at low clearance and cost ~50x the mean tile; rows that look up cost nothing.  Start the expensive rows
+	// first (cost proxy 1/|dir.z| of the centre ray for dir.z < 0).  Depends on the view geometry only, not on the
+	// camera position or heading, so a flythrough computes it once.
+	P.row_order = NULL;
+	if (f->projection != HMRM_ORTHOGRAPHIC && P.tiles_y > 1 && !std::getenv("HMRM_NO_ROW_ORDER")) {
+		const double key[8] = {(double)f->projection, (double)W, (double)H, f->vang, f->hfov, (double)row_begin,
+		                       (double)(P.tile_y_first * 65536 + P.tile_y_step), (double)P.tiles_y};
+		if (!c->row_key_valid || std::memcmp(key, c->row_key, sizeof key) != 0) {
+			std::vector<std::pair<double, int> > cost((size_t)P.tiles_y);
+			for (int t = 0; t < P.tiles_y; ++t) {
+				int py = row_begin + (P.tile_y_first + t * P.tile_y_step) * 4 + 2;
+				if (py > H - 1) py = H - 1;
+				Vec3 pos, dir;
+				plane_ray(pc, 0.5, (double)py / (H - 1), &pos, &dir);
+				const double dz = dir.z;
+				cost[(size_t)t].first = (dz < 0.0) ? -1.0 / std::fmax(-dz, 1e-3) : 1.0 + dz;   // ascending sort key
+				cost[(size_t)t].second = t;
+			}
+			std::stable_sort(cost.begin(), cost.end());
+			std::vector<int> order((size_t)P.tiles_y);
+			for (int t = 0; t < P.tiles_y; ++t) order[(size_t)t] = cost[(size_t)t].second;
+			if (P.tiles_y > c->row_order_cap) {
+				HMRM_CUDA(c, cudaStreamSynchronize(stream));
+				cudaFree(c->d_row_order);
+				c->d_row_order = NULL;
+				HMRM_CUDA(c, cudaMalloc(&c->d_row_order, (size_t)P.tiles_y * sizeof(int)));
+				c->row_order_cap = P.tiles_y;
+			}
+			// the previous schedule may still be read by a kernel in flight on this stream: order the copy after it
+			HMRM_CUDA(c, cudaMemcpyAsync(c->d_row_order, order.data(), (size_t)P.tiles_y * sizeof(int),
+			                             cudaMemcpyHostToDevice, stream));
+			HMRM_CUDA(c, cudaStreamSynchronize(stream));
+			std::memcpy(c->row_key, key, sizeof key);
+			c->row_key_valid = true;
+		}
+		P.row_order = c->d_row_order;
+	}
+
+	// FP32 miss prefilter (see ray_setup.cuh:fast_miss): the box inflated by 2^-12 of the scene scale
+	P.fast_setup = (f->precision == HMRM_FP32_FAST) ? 1 : 0;
+	{
+		const bool relative = f->projection != HMRM_ORTHOGRAPHIC;      // bounds relative to the camera position
+		double scale = 0.0;
+		for (int i = 0; i < 3; ++i) {
+			scale = std::fmax(scale, std::fmax(std::fabs(P.c0[i]), std::fabs(P.c1[i])));
+			scale = std::fmax(scale, std::fabs(P.cam[i]));
+			scale = std::fmax(scale, std::fabs(P.ul[i]) + std::fabs(P.pr[i]) + std::fabs(P.pd[i]));
+		}
+		const double delta = std::ldexp(scale, -12);
+		for (int i = 0; i < 3; ++i) {
+			const double lo = std::fmin(P.c0[i], P.c1[i]) - delta, hi = std::fmax(P.c0[i], P.c1[i]) + delta;
+			const double org = relative ? P.cam[i] : 0.0;
+			P.fs_b0[i] = (float)(lo - org);
+			P.fs_b1[i] = (float)(hi - org);
+			P.fs_ul[i] = (float)P.ul[i];
+			P.fs_pr[i] = (float)P.pr[i];
+			P.fs_pd[i] = (float)P.pd[i];
+		}
+		if (!std::isfinite(scale) || !(delta > 0.0)) P.fast_setup = 0;
+	}
+
 	P.surf = c->d_surf;
 	P.color = c->d_color;
 	P.fb = d_out;
@@ -405,8 +474,15 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 
 	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_begin, stream));
 	if (traversal == HMRM_TRAVERSAL_SKIP) {
-		if (want_stats || want_steps) k2_render_skip<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
-		else k2_render_skip<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		const bool stats_kernel = want_stats || want_steps;
+		if (P.fast_setup) {
+			if (stats_kernel) k2_render_skip<true, true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+			else k2_render_skip<false, true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		}
+		else {
+			if (stats_kernel) k2_render_skip<true, false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+			else k2_render_skip<false, false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		}
 	}
 	else {
 		if (want_stats) k2_render_brute<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
@@ -495,6 +571,9 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->slot = 0;
 	c->d_step_index = NULL;
 	c->step_index_cap = 0;
+	c->d_row_order = NULL;
+	c->row_order_cap = 0;
+	c->row_key_valid = false;
 	c->d_stats = NULL;
 	c->d_tile_counter = NULL;
 	c->last_had_stats = c->last_had_step_index = c->timing_valid = false;
@@ -545,6 +624,7 @@ void hmrm_destroy(hmrm_ctx *c) {
 	}
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	cudaFree(c->d_step_index);
+	cudaFree(c->d_row_order);
 	cudaFree(c->d_stats);
 	cudaFree(c->d_tile_counter);
 	if (c->ev_begin) cudaEventDestroy(c->ev_begin);
@@ -814,13 +894,13 @@ int hmrm_get_stats(hmrm_ctx *c, hmrm_stats *out) {
 	return HMRM_OK;
 }
 
-int hmrm_get_debug_counters(hmrm_ctx *c, int64_t out[8]) {
+int hmrm_get_debug_counters(hmrm_ctx *c, int64_t out[12]) {
 	if (!c || !out) return HMRM_ERR_INVALID;
 	HMRM_CUDA(c, cudaSetDevice(c->device));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
 	DeviceStats ds;
 	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats, sizeof ds, cudaMemcpyDeviceToHost));
-	for (int i = 0; i < 8; ++i) out[i] = (int64_t)ds.dbg[i];
+	for (int i = 0; i < 12; ++i) out[i] = (int64_t)ds.dbg[i];
 	return HMRM_OK;
 }
 

@@ -169,12 +169,13 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 		hi = (int)min((unsigned)(b + 2) << sh, grid);
 	};
 
-	unsigned steps = 0u, fetches = 0u;
+	unsigned steps = 0u, fetches = 0u, iters = 0u;
 	int level = P.lstart;
 	MarchPos cur = locate(P, ax.p, ay.p, az.p);
 
 	while ((unsigned)cur.vx < grid_vx && (unsigned)cur.vy < grid_vy) {       // :1006-1011
 		// ---- A: find a level whose neighbourhood this sample clears (descend), or reach the cell itself ----
+		if (kStats) iters += 1u;
 		int q = probe(level, cur.vx, cur.vy);
 		if (kStats) fetches += 1u;
 		while (cur.zq <= q && level > 0) {
@@ -307,9 +308,12 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 	}
 	tally.steps = steps;
 	tally.fetches = fetches;
+	if (kStats) atomicMax(&P.stats->dbg[10], (unsigned long long)iters);    // most loop iterations of any ray
 }
 
-template <bool kStats>
+// kFast: HMRM_FP32_FAST front end (ray_setup.cuh:fast_miss) — a separate instantiation, because merging the filter
+// into the exact kernel behind a run-time flag made ptxas spill in the march loop (terrain frames 0.79 -> 1.5 ms).
+template <bool kStats, bool kFast>
 __global__ void __launch_bounds__(256, 4) k2_render_skip(const __grid_constant__ RenderParams P) {
 	const int lane = threadIdx.x & 31;
 	const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
@@ -317,30 +321,42 @@ __global__ void __launch_bounds__(256, 4) k2_render_skip(const __grid_constant__
 	for (;;) {
 		const unsigned tile = next_tile(P.tile_counter);
 		if (tile >= n_tiles) break;
-		const int ty = (int)(tile / (unsigned)P.tiles_x);
-		const int tx = (int)(tile - (unsigned)ty * (unsigned)P.tiles_x);
+		const int ty_seq = (int)(tile / (unsigned)P.tiles_x);
+		const int tx = (int)(tile - (unsigned)ty_seq * (unsigned)P.tiles_x);
+		// longest-processing-time-first: a few grazing tiles take ~50x the mean, so they must start early
+		const int ty = P.row_order ? __ldg(P.row_order + ty_seq) : ty_seq;
 		const int px = tx * 8 + (lane & 7);
 		const int py = P.row_begin + (P.tile_y_first + ty * P.tile_y_step) * 4 + (lane >> 3);
 		const bool active = pixel_selected(P, px, py);
+		long long t_tile = 0;
+		if (kStats) t_tile = clock64();
 
 		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u, {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};
 		if (active) {
-			const Ray ray = generate_ray(P, px, py);
 			uint32_t rgba = 0u;
 			bool real_hit = false;
 			int first_hit = -1;
-			double ex, ey, ez;
-			if (box_entry(P, ray, ex, ey, ez)) {
-				tally.box_hit = 1u;
-				first_hit = -2;
-				march_skip<kStats>(P, ray, ex, ey, ez, rgba, real_hit, first_hit, tally);
+			if (!(kFast && fast_miss(P, px, py, rgba))) {
+				const Ray ray = generate_ray(P, px, py);
+				double ex, ey, ez;
+				if (box_entry(P, ray, ex, ey, ez)) {
+					tally.box_hit = 1u;
+					first_hit = -2;
+					march_skip<kStats>(P, ray, ex, ey, ez, rgba, real_hit, first_hit, tally);
+				}
+				if (!real_hit) rgba = miss_colour(P, ray.dz);
+				else tally.surf_hit = 1u;
 			}
-			if (!real_hit) rgba = miss_colour(P, ray.dz);
-			else tally.surf_hit = 1u;
 			P.fb[(size_t)py * (size_t)P.W + (size_t)px] = rgba;
 			if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
 		}
 		commit_tally<kStats>(P, active, tally);
+		if (kStats && lane == 0) {
+			const unsigned long long dt = (unsigned long long)(clock64() - t_tile);
+			atomicMax(&P.stats->dbg[8], dt);       // slowest tile (SM clocks)
+			atomicAdd(&P.stats->dbg[9], dt);       // sum over tiles
+			if (dt > 100000ULL) atomicAdd(&P.stats->dbg[11], 1ULL);   // tiles above 100 k clocks
+		}
 	}
 }
 

@@ -111,6 +111,95 @@ __device__ __forceinline__ uint32_t hit_colour(const RenderParams &P, uint32_t t
 	return ((texel >> 24) == 0u) ? P.bg_rgba : (texel | 0xFF000000u);
 }
 
+// ---- FP32 prefilter for rays that miss the box (HMRM_FP32_FAST) ---------------------------------------------
+//
+// Most rays of a frame never touch the terrain box; for them the exact front end (six FP64 divides for the slab
+// test, a square root and a divide for the normalisation) only has to deliver (a) the verdict "miss" and (b) the
+// sky colour.  This filter decides both in FP32 when it can PROVE the FP64 result, and otherwise says "unknown"
+// and the exact path runs.  It never changes a pixel:
+//  (a) the slab test is run against the box inflated by fs_delta = 2^-12 x (scene scale) — about 10^3 times the
+//      worst FP32 evaluation error and 10^9 times the reference's own FP64 rounding — so "misses the inflated box
+//      in FP32" implies "the reference's FP64 comparison chain reports a miss".  Rays with a near-zero direction
+//      component (inf/NaN territory of src/AABB.cpp:58-59) are left to the exact path.
+//  (b) the colour channels floor(clamp(220 z^2 + bg)) etc. (main/hmap.cpp:1044-1051) are taken from FP32 only
+//      when the value is at least 3e-4 away from the next integer; z comes from the exactly computed FP64 ray
+//      vector with one float rsqrt (relative error < 3e-7 => channel error < 1.5e-4).
+__device__ __forceinline__ float approx_rcp(float x) {
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+__device__ __forceinline__ float approx_rsqrt(float x) {
+	float r;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
+__device__ __forceinline__ bool fast_channel(float c, uint32_t &out) {
+	if (c >= 255.001f) { out = 255u; return true; }
+	const float fl = floorf(c);
+	const float d = c - fl;
+	out = (uint32_t)fl;
+	return d > 3.0e-4f && d < 1.0f - 3.0e-4f && c < 254.999f;
+}
+
+// true: the pixel is a proven miss and `rgba` is its (proven) colour.  false: run the exact path.
+__device__ __forceinline__ bool fast_miss(const RenderParams &P, int px, int py, uint32_t &rgba) {
+	float vx, vy, vz;          // ray direction (any length)
+	float ox = 0.f, oy = 0.f, oz = 0.f;   // ray origin relative to the frame of fs_b0/fs_b1
+	double dz_exact = 0.0;     // spherical / orthographic: the exact z of the unit direction is already at hand
+	double vzd = 0.0, len2d = 1.0;
+	if (P.projection == 1) {
+		const double w = __ldg(P.wtab + px), h = __ldg(P.htab + py);
+		const double dx = fsub(fadd(fadd(P.ul[0], fmul(w, P.pr[0])), fmul(h, P.pd[0])), P.cam[0]);
+		const double dy = fsub(fadd(fadd(P.ul[1], fmul(w, P.pr[1])), fmul(h, P.pd[1])), P.cam[1]);
+		vzd = fsub(fadd(fadd(P.ul[2], fmul(w, P.pr[2])), fmul(h, P.pd[2])), P.cam[2]);
+		len2d = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(vzd, vzd));
+		vx = (float)dx; vy = (float)dy; vz = (float)vzd;
+	}
+	else if (P.projection == 2) {
+		const float sv = (float)__ldg(P.sin_va + py);
+		vx = sv * (float)__ldg(P.cos_ha + px);
+		vy = sv * (float)__ldg(P.sin_ha + px);
+		dz_exact = __ldg(P.cos_va + py);
+		vz = (float)dz_exact;
+	}
+	else {
+		const float w = (float)__ldg(P.wtab + px), h = (float)__ldg(P.htab + py);
+		ox = fmaf(h, P.fs_pd[0], fmaf(w, P.fs_pr[0], P.fs_ul[0]));
+		oy = fmaf(h, P.fs_pd[1], fmaf(w, P.fs_pr[1], P.fs_ul[1]));
+		oz = fmaf(h, P.fs_pd[2], fmaf(w, P.fs_pr[2], P.fs_ul[2]));
+		vx = (float)P.look[0]; vy = (float)P.look[1]; vz = (float)P.look[2];
+		dz_exact = P.look[2];
+	}
+	const float ax = fabsf(vx), ay = fabsf(vy), az = fabsf(vz);
+	const float vmax = fmaxf(ax, fmaxf(ay, az));
+	if (!(fminf(ax, fminf(ay, az)) > vmax * 1.0e-6f) || !(vmax < 1.0e18f)) return false;
+
+	const float rx = approx_rcp(vx), ry = approx_rcp(vy), rz = approx_rcp(vz);
+	const float tx0 = (P.fs_b0[0] - ox) * rx, tx1 = (P.fs_b1[0] - ox) * rx;
+	const float ty0 = (P.fs_b0[1] - oy) * ry, ty1 = (P.fs_b1[1] - oy) * ry;
+	const float tz0 = (P.fs_b0[2] - oz) * rz, tz1 = (P.fs_b1[2] - oz) * rz;
+	const float lo = fmaxf(fminf(tx0, tx1), fmaxf(fminf(ty0, ty1), fminf(tz0, tz1)));
+	const float hi = fminf(fmaxf(tx0, tx1), fminf(fmaxf(ty0, ty1), fmaxf(tz0, tz1)));
+	if (!((lo > hi) || (hi < 0.0f))) return false;      // may touch the (inflated) box: exact path
+
+	if (P.projection != 1) {
+		rgba = miss_colour(P, dz_exact);                   // exact, and cheap: no normalisation needed
+		return true;
+	}
+	const float zf = (float)vzd * approx_rsqrt((float)len2d);
+	if (fabsf(zf) < 1.0e-5f) return false;                // sign of dir.z not provable
+	if (zf < 0.0f) { rgba = P.bg_rgba; return true; }
+	const float zz = zf * zf;
+	uint32_t r, g, b;
+	const bool ok = fast_channel(fmaf(220.0f, zz, (float)P.bg[0]), r) & fast_channel(fmaf(240.0f, zz, (float)P.bg[1]), g) &
+	                fast_channel(fmaf(255.0f, zf, (float)P.bg[2]), b);
+	if (!ok) return false;
+	rgba = r | (g << 8) | (b << 16) | 0xFF000000u;
+	return true;
+}
+
 } // namespace hmrm
 
 #endif

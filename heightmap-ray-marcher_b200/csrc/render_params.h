@@ -17,7 +17,7 @@ struct DeviceStats {
 	unsigned long long max_steps;
 	unsigned int status;           // HMRM_ERR_NONTERMINATING if a ray was cut off
 	unsigned int pad;
-	unsigned long long dbg[8];     // traversal diagnostics (stats mode only), see hmrm_get_debug_counters
+	unsigned long long dbg[12];    // traversal diagnostics (stats mode only), see hmrm_get_debug_counters
 };
 
 struct RenderParams {
@@ -28,6 +28,7 @@ struct RenderParams {
 	int cycle, period;
 	int tiles_x, tiles_y;          // 8x4-pixel tiles this launch renders
 	int tile_y_first, tile_y_step; // launch tile row t is frame tile row tile_y_first + t * tile_y_step (row interleave)
+	const int *row_order;          // optional permutation of the launch tile rows: expensive (grazing) rows first
 	// map
 	int map_w, map_h;
 	// image plane (host-built, frame_setup.h)
@@ -59,6 +60,10 @@ struct RenderParams {
 	const uint16_t *lv;            // all levels back to back: level 0 = Zq(surf) per cell (row-major [map_h][map_w]),
 	                               // level l >= 1 = max of level 0 over the 2^l x 2^l block and its eight neighbours
 	uint2 lv_desc[16];             // per level: (element offset into lv, row pitch)
+	// ---- FP32 miss prefilter (HMRM_FP32_FAST): slab bounds of the box inflated by 2^-12 of the scene scale ----
+	int fast_setup;                // 0 = off (pure FP64 front end)
+	float fs_b0[3], fs_b1[3];      // inflated box, b0 < b1 per axis; relative to cam for perspective / spherical
+	float fs_ul[3], fs_pr[3], fs_pd[3];   // orthographic ray origin plane, as floats
 	uint32_t bg_rgba;              // bg colour with alpha 255
 	uint8_t bg[3];
 	uint8_t pad;

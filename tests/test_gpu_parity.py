@@ -189,6 +189,48 @@ def test_quantiser_range_never_affects_results(hmrm, oracle, name, shrink, monke
     assert (st.steps, st.surf_hits, st.box_hits) == (ost.steps, ost.surf_hits, ost.box_hits)
 
 
+@pytest.mark.parametrize("scene", S.SCENES, ids=lambda s: s["name"])
+def test_fp32_fast_mode_tolerance(hmrm, renderer, oracle, scene):
+    """HMRM_FP32_FAST (north star: >= 99.5 % of pixels identical to the reference frame, every other pixel explained
+    by a first-hit step index differing by at most 1).  The mode only uses FP32 as a filter with FP64 fallbacks, so
+    the expected outcome is stronger: every pixel and every step index identical.  Tolerance written out anyway."""
+    maps = H.load_scene_maps(scene, oracle)
+    H.configure(renderer, scene, maps)
+    f = H.product_frame(hmrm, renderer, scene, precision=hmrm.FP32_FAST, flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX)
+    got = renderer.render(f)
+    steps = renderer.step_index(f)
+    want = H.golden_frames()[scene["name"]]
+    _, osteps, ost = H.oracle_render_scene(oracle, scene, maps)
+    differs = (got != want).any(axis=2)
+    assert 1.0 - differs.mean() >= 0.995
+    assert (np.abs(steps[differs].astype(np.int64) - osteps[differs]) <= 1).all()
+    assert not differs.any() and np.array_equal(steps, osteps)        # what the construction actually guarantees
+    assert renderer.stats().steps == ost.steps
+
+
+@pytest.mark.parametrize("proj", [1, 2, 3])
+def test_fp32_fast_mode_equals_exact_on_random_cameras(hmrm, renderer, oracle, proj):
+    """Randomised views (many of them mostly sky / mostly outside the map): FAST == EXACT bit for bit."""
+    renderer.lum_r, renderer.lum_g, renderer.lum_b = S.DEFAULT_LUM
+    renderer.min_height, renderer.max_height = 0.0, 10.0
+    renderer.synth_maps(10, 99)
+    rng = np.random.RandomState(1000 + proj)
+    for i in range(24):
+        kw = dict(projection=proj, screen_width=int(rng.randint(64, 700)), screen_height=int(rng.randint(48, 400)),
+                  cam_pos=(rng.uniform(-15, 25), rng.uniform(-25, 15), rng.uniform(-5, 40)),
+                  hang=rng.uniform(-3.2, 3.2), vang=rng.uniform(0.0, 3.14159), hfov=rng.uniform(0.3, 2.9),
+                  grid_width=0.01, step_dist=float(rng.choice([0.05, 0.013, 0.2])), ortho_width=rng.uniform(0.005, 0.08),
+                  bg=(int(rng.randint(0, 256)), int(rng.randint(0, 256)), int(rng.randint(0, 256))),
+                  flags=hmrm.FLAG_STEP_INDEX)
+        fe = renderer.frame(precision=hmrm.FP64_EXACT, **kw)
+        a = renderer.render(fe).copy()
+        ia = renderer.step_index(fe)
+        ff = renderer.frame(precision=hmrm.FP32_FAST, **kw)
+        b = renderer.render(ff).copy()
+        ib = renderer.step_index(ff)
+        assert np.array_equal(a, b) and np.array_equal(ia, ib), f"camera {i}: {int((a != b).any(axis=2).sum())} pixels"
+
+
 def test_invalid_arguments_are_rejected(hmrm, renderer, oracle):
     scene = S.SCENE_BY_NAME["persp_basic"]
     H.configure(renderer, scene, H.load_scene_maps(scene, oracle))

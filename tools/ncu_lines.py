@@ -69,8 +69,8 @@ def main():
             cur["hdr"] = r
         elif cur is not None and cur["hdr"] and len(r) == len(cur["hdr"]):
             cur["rows"].append(r)
-    blk = next(b for b in blocks if args.kernel.replace("ILb0", "<(bool)0>").replace("ILb1", "<(bool)1>") in b["name"]
-               or args.kernel in b["name"])
+    base = args.kernel.split("ILb")[0]
+    blk = next(b for b in blocks if base in b["name"])
     hdr = blk["hdr"]
     col = {h: i for i, h in enumerate(hdr)}
     lines = sass_lines(args.kernel)

@@ -16,6 +16,7 @@ ap.add_argument("--traversal", default="skip")
 ap.add_argument("--frames", type=int, default=4)
 ap.add_argument("--first", type=int, default=0)
 ap.add_argument("--stats", action="store_true")
+ap.add_argument("--fast", action="store_true", help="HMRM_FP32_FAST")
 ap.add_argument("--vang", type=float, default=None, help="override vang (degrees), e.g. 30 = all sky")
 args = ap.parse_args()
 
@@ -31,7 +32,7 @@ for i in range(args.frames):
         c["vang_deg"] = args.vang
     f = r.frame(projection=wl["projection"], screen_width=wl["W"], screen_height=wl["H"], cam_pos=c["pos"],
                 hang=hmrm.deg2rad(c["hang_deg"]), vang=hmrm.deg2rad(c["vang_deg"]), hfov=hmrm.deg2rad(c["hfov_deg"]),
-                ortho_width=c["ortho_width"], grid_width=bench.GRID_WIDTH, step_dist=wl["step_dist"], traversal=trav,
+                ortho_width=c["ortho_width"], grid_width=bench.GRID_WIDTH, step_dist=wl["step_dist"], traversal=trav, precision=1 if args.fast else 0,
                 flags=hmrm.FLAG_STATS if args.stats else 0)
     out = r.render(f)
     st = r.stats()
@@ -42,4 +43,6 @@ for i in range(args.frames):
         d = r.debug_counters()
         print("   jumps %d (covering %d samples, %.1f/jump) plain-above %d descents %d cell-above %d cell-below %d refused %d slow-locate %d"
               % (d[0], d[1], d[1] / max(d[0], 1), d[2], d[3], d[4], d[5], d[6], d[7]))
+        print("   slowest tile %d clk (%.1f us at 1.965 GHz), mean tile %.0f clk, tiles > 100k clk: %d, most iterations of a ray: %d"
+              % (d[8], d[8] / 1965.0, d[9] / max(st.rays / 32, 1), d[11], d[10]))
 r.close()
