@@ -31,6 +31,8 @@ namespace {
 
 std::string g_create_error;
 
+const int kLaunchSlots = 4;
+
 struct Staging {
 	double *host;          // pinned
 	size_t cap;            // doubles
@@ -43,8 +45,8 @@ struct Staging {
 struct hmrm_ctx {
 	int device;
 	int num_sms;
-	cudaStream_t stream;
-	cudaEvent_t ev_begin, ev_end;
+	cudaStream_t stream;          // compute stream of frame-buffer slot 0 (and of everything that is not a frame)
+	cudaStream_t stream_alt;      // compute stream of frame-buffer slot 1: frame n+1 starts while frame n's tail drains
 	std::string err;
 
 	// maps
@@ -68,7 +70,7 @@ struct hmrm_ctx {
 	// per-resolution tables
 	int tab_w, tab_h;
 	std::vector<double> wtab, htab, sph;
-	double *d_wtab, *d_htab, *d_sph;
+	double *d_wtab, *d_htab, *d_sph[2];   // spherical tables are double-buffered like their staging
 	size_t sph_cap;
 	Staging staging[2];
 	int staging_next;
@@ -88,8 +90,11 @@ struct hmrm_ctx {
 	int row_order_cap;
 	double row_key[8];
 	bool row_key_valid;
-	DeviceStats *d_stats;
-	unsigned int *d_tile_counter;
+	// per-launch resources, used round-robin so that up to kLaunchSlots kernels of this context may be in flight
+	DeviceStats *d_stats[kLaunchSlots];
+	unsigned int *d_tile_counter[kLaunchSlots];
+	cudaEvent_t ev_begin[kLaunchSlots], ev_end[kLaunchSlots];
+	int launch_next, launch_last;
 	bool last_had_stats, last_had_step_index, timing_valid;
 	int last_w, last_h;
 	cudaStream_t last_stream;    // stream of the most recent render (the caller's, for hmrm_render_device)
@@ -132,6 +137,13 @@ __global__ void __launch_bounds__(256) k_synth_maps(uint32_t log2n, uint32_t see
 	}
 }
 
+int drain(hmrm_ctx *c) {
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream_alt));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	return HMRM_OK;
+}
+
 void free_maps(hmrm_ctx *c) {
 	cudaFree(c->d_rgb);
 	cudaFree(c->d_color);
@@ -150,6 +162,7 @@ int alloc_maps(hmrm_ctx *c, int32_t w, int32_t h) {
 	if (w < 1 || h < 1 || w > 32768 || h > 32768)
 		return fail(c, HMRM_ERR_INVALID, "map size %dx%d outside [1,32768]", w, h);
 	HMRM_CUDA(c, cudaSetDevice(c->device));
+	if (int rc = drain(c)) return rc;
 	if (c->maps_set && c->map_w == w && c->map_h == h) {
 		c->heights_set = false;
 		return HMRM_OK;
@@ -182,7 +195,7 @@ int alloc_maps(hmrm_ctx *c, int32_t w, int32_t h) {
 
 int ensure_tables(hmrm_ctx *c, int W, int H) {
 	if (c->tab_w == W && c->tab_h == H) return HMRM_OK;
-	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (int rc = drain(c)) return rc;
 	cudaFree(c->d_wtab);
 	cudaFree(c->d_htab);
 	c->d_wtab = c->d_htab = NULL;
@@ -194,10 +207,10 @@ int ensure_tables(hmrm_ctx *c, int W, int H) {
 	HMRM_CUDA(c, cudaMemcpy(c->d_htab, c->htab.data(), (size_t)H * 8, cudaMemcpyHostToDevice));
 	const size_t need = (size_t)(2 * W + 2 * H);
 	if (need > c->sph_cap) {
-		cudaFree(c->d_sph);
-		c->d_sph = NULL;
-		HMRM_CUDA(c, cudaMalloc(&c->d_sph, need * 8));
 		for (int i = 0; i < 2; ++i) {
+			cudaFree(c->d_sph[i]);
+			c->d_sph[i] = NULL;
+			HMRM_CUDA(c, cudaMalloc(&c->d_sph[i], need * 8));
 			if (c->staging[i].host) cudaFreeHost(c->staging[i].host);
 			c->staging[i].host = NULL;
 			HMRM_CUDA(c, cudaMallocHost(&c->staging[i].host, need * 8));
@@ -213,8 +226,7 @@ int ensure_tables(hmrm_ctx *c, int W, int H) {
 
 int ensure_framebuffer(hmrm_ctx *c, int W, int H) {
 	if (c->d_fb && c->fb_w == W && c->fb_h == H) return HMRM_OK;
-	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
-	HMRM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	if (int rc = drain(c)) return rc;
 	c->copy_pending[0] = c->copy_pending[1] = false;
 	cudaFree(c->d_fb);
 	cudaFree(c->d_fb_alt);
@@ -320,7 +332,8 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	P.htab = c->d_htab;
 
 	if (f->projection == HMRM_SPHERICAL) {
-		Staging &st = c->staging[c->staging_next];
+		const int si = c->staging_next;
+		Staging &st = c->staging[si];
 		c->staging_next ^= 1;
 		if (st.pending) {
 			HMRM_CUDA(c, cudaEventSynchronize(st.consumed));
@@ -328,13 +341,13 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		}
 		fill_spherical_tables(pc, W, H, c->wtab, c->htab, &c->sph);
 		std::memcpy(st.host, c->sph.data(), c->sph.size() * 8);
-		HMRM_CUDA(c, cudaMemcpyAsync(c->d_sph, st.host, c->sph.size() * 8, cudaMemcpyHostToDevice, stream));
+		HMRM_CUDA(c, cudaMemcpyAsync(c->d_sph[si], st.host, c->sph.size() * 8, cudaMemcpyHostToDevice, stream));
 		HMRM_CUDA(c, cudaEventRecord(st.consumed, stream));
 		st.pending = true;
-		P.cos_ha = c->d_sph;
-		P.sin_ha = c->d_sph + W;
-		P.sin_va = c->d_sph + 2 * W;
-		P.cos_va = c->d_sph + 2 * W + H;
+		P.cos_ha = c->d_sph[si];
+		P.sin_ha = c->d_sph[si] + W;
+		P.sin_va = c->d_sph[si] + 2 * W;
+		P.cos_va = c->d_sph[si] + 2 * W + H;
 	}
 
 	// Tile-row schedule: rows whose rays graze the terrain (direction just below the horizon) march for hundreds of
@@ -359,6 +372,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 			std::stable_sort(cost.begin(), cost.end());
 			std::vector<int> order((size_t)P.tiles_y);
 			for (int t = 0; t < P.tiles_y; ++t) order[(size_t)t] = cost[(size_t)t].second;
+			if (int rc2 = drain(c)) return rc2;         // a kernel in flight may still read the old schedule
 			if (P.tiles_y > c->row_order_cap) {
 				HMRM_CUDA(c, cudaStreamSynchronize(stream));
 				cudaFree(c->d_row_order);
@@ -421,11 +435,13 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		HMRM_CUDA(c, cudaMemsetAsync(c->d_step_index, 0xFD, need * 4, stream));   // -3 = not rendered... bytes FD
 		P.step_index = c->d_step_index;
 	}
-	P.stats = c->d_stats;
-	P.tile_counter = c->d_tile_counter;
+	const int ls = c->launch_next;
+	c->launch_next = (ls + 1) % kLaunchSlots;
+	P.stats = c->d_stats[ls];
+	P.tile_counter = c->d_tile_counter[ls];
 
-	HMRM_CUDA(c, cudaMemsetAsync(c->d_tile_counter, 0, sizeof(unsigned int), stream));
-	HMRM_CUDA(c, cudaMemsetAsync(c->d_stats, 0, sizeof(DeviceStats), stream));
+	HMRM_CUDA(c, cudaMemsetAsync(c->d_tile_counter[ls], 0, sizeof(unsigned int), stream));
+	HMRM_CUDA(c, cudaMemsetAsync(c->d_stats[ls], 0, sizeof(DeviceStats), stream));
 
 	int traversal = f->traversal;
 	if (traversal == HMRM_TRAVERSAL_AUTO) traversal = c->skip_ready ? HMRM_TRAVERSAL_SKIP : HMRM_TRAVERSAL_BRUTE;
@@ -472,7 +488,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	if (blocks > max_useful) blocks = max_useful;
 	if (blocks < 1) blocks = 1;
 
-	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_begin, stream));
+	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_begin[ls], stream));
 	if (traversal == HMRM_TRAVERSAL_SKIP) {
 		const bool stats_kernel = want_stats || want_steps;
 		if (P.fast_setup) {
@@ -489,7 +505,8 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		else k2_render_brute<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
 	}
 	HMRM_CUDA(c, cudaGetLastError());
-	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_end, stream));
+	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_end[ls], stream));
+	c->launch_last = ls;
 
 	c->last_stream = stream;
 	c->last_had_stats = want_stats;
@@ -534,6 +551,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->device = device;
 	c->num_sms = prop.multiProcessorCount;
 	c->stream = NULL;
+	c->stream_alt = NULL;
 	c->last_stream = NULL;
 	c->map_w = c->map_h = 0;
 	c->d_rgb = NULL;
@@ -554,7 +572,8 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->zq_offset = HMRM_MAGIC;
 	c->skip_ready = false;
 	c->tab_w = c->tab_h = 0;
-	c->d_wtab = c->d_htab = c->d_sph = NULL;
+	c->d_wtab = c->d_htab = NULL;
+	c->d_sph[0] = c->d_sph[1] = NULL;
 	c->sph_cap = 0;
 	for (int i = 0; i < 2; ++i) {
 		c->staging[i].host = NULL;
@@ -574,8 +593,12 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->d_row_order = NULL;
 	c->row_order_cap = 0;
 	c->row_key_valid = false;
-	c->d_stats = NULL;
-	c->d_tile_counter = NULL;
+	for (int i = 0; i < kLaunchSlots; ++i) {
+		c->d_stats[i] = NULL;
+		c->d_tile_counter[i] = NULL;
+		c->ev_begin[i] = c->ev_end[i] = NULL;
+	}
+	c->launch_next = c->launch_last = 0;
 	c->last_had_stats = c->last_had_step_index = c->timing_valid = false;
 	c->last_w = c->last_h = 0;
 	c->last_stream = NULL;
@@ -586,12 +609,15 @@ int hmrm_create(int device, hmrm_ctx **out) {
 		err = cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming);
 		if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
 	}
-	if (err == cudaSuccess) err = cudaEventCreate(&c->ev_begin);
-	if (err == cudaSuccess) err = cudaEventCreate(&c->ev_end);
+	if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->stream_alt, cudaStreamNonBlocking);
+	for (int i = 0; i < kLaunchSlots && err == cudaSuccess; ++i) {
+		err = cudaEventCreate(&c->ev_begin[i]);
+		if (err == cudaSuccess) err = cudaEventCreate(&c->ev_end[i]);
+		if (err == cudaSuccess) err = cudaMalloc(&c->d_stats[i], sizeof(DeviceStats));
+		if (err == cudaSuccess) err = cudaMalloc(&c->d_tile_counter[i], 256);
+	}
 	for (int i = 0; i < 2 && err == cudaSuccess; ++i)
 		err = cudaEventCreateWithFlags(&c->staging[i].consumed, cudaEventDisableTiming);
-	if (err == cudaSuccess) err = cudaMalloc(&c->d_stats, sizeof(DeviceStats));
-	if (err == cudaSuccess) err = cudaMalloc(&c->d_tile_counter, 256);
 	if (err == cudaSuccess) err = cudaMalloc(&c->d_max_bits, 32);
 	if (err != cudaSuccess) {
 		fail(NULL, HMRM_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));
@@ -606,12 +632,13 @@ void hmrm_destroy(hmrm_ctx *c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->stream_alt) cudaStreamSynchronize(c->stream_alt);
 	free_maps(c);
 	cudaFree(c->d_max_bits);
 	cudaFree(c->d_wtab);
 	cudaFree(c->d_htab);
-	cudaFree(c->d_sph);
 	for (int i = 0; i < 2; ++i) {
+		cudaFree(c->d_sph[i]);
 		if (c->staging[i].host) cudaFreeHost(c->staging[i].host);
 		if (c->staging[i].consumed) cudaEventDestroy(c->staging[i].consumed);
 	}
@@ -625,11 +652,14 @@ void hmrm_destroy(hmrm_ctx *c) {
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	cudaFree(c->d_step_index);
 	cudaFree(c->d_row_order);
-	cudaFree(c->d_stats);
-	cudaFree(c->d_tile_counter);
-	if (c->ev_begin) cudaEventDestroy(c->ev_begin);
-	if (c->ev_end) cudaEventDestroy(c->ev_end);
+	for (int i = 0; i < kLaunchSlots; ++i) {
+		cudaFree(c->d_stats[i]);
+		cudaFree(c->d_tile_counter[i]);
+		if (c->ev_begin[i]) cudaEventDestroy(c->ev_begin[i]);
+		if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
+	}
 	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->stream_alt) cudaStreamDestroy(c->stream_alt);
 	delete c;
 }
 
@@ -689,6 +719,7 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 	if (!lum || !finite3(lum) || !std::isfinite(min_height) || !std::isfinite(max_height))
 		return fail(c, HMRM_ERR_INVALID, "lum, min_height and max_height must be finite");
 	HMRM_CUDA(c, cudaSetDevice(c->device));
+	if (int rc = drain(c)) return rc;
 	PrepassParams q;
 	q.lum_r = lum[0];
 	q.lum_g = lum[1];
@@ -821,17 +852,25 @@ int hmrm_render_async(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
 	if (rc) return rc;
 	// Whole frames (cycle_period 1) alternate between two device buffers so that the copy-out of frame n overlaps
 	// the kernel of frame n+1; the progressive interleave (cycle_period > 1) accumulates in the one persistent buffer.
-	const int slot = (f->cycle_period == 1) ? (c->slot ^ 1) : 0;
+	// Each buffer has its own compute stream, so the kernel of frame n+1 starts filling SMs as the CTAs of frame n
+	// run out of tiles (a handful of grazing tiles take ~50x the mean: the tail of a frame leaves most SMs idle).
+	const bool whole = f->cycle_period == 1 && (f->flags & HMRM_FLAG_STEP_INDEX) == 0;
+	const int slot = whole ? (c->slot ^ 1) : 0;
 	uint32_t *fb = slot ? c->d_fb_alt : c->d_fb;
-	if (c->copy_pending[slot]) HMRM_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
-	if (f->cycle_period != 1 && c->slot == 1) {
-		// the newest picture lives in the alternate buffer: a progressive frame must land on top of it
-		HMRM_CUDA(c, cudaMemcpyAsync(c->d_fb, c->d_fb_alt, (size_t)c->fb_w * (size_t)c->fb_h * 4, cudaMemcpyDeviceToDevice,
-		                             c->stream));
+	cudaStream_t cs = slot ? c->stream_alt : c->stream;
+	if (!whole) {
+		// progressive frames and step-index captures are ordered after everything else
+		HMRM_CUDA(c, cudaStreamSynchronize(c->stream_alt));
+		if (f->cycle_period != 1 && c->slot == 1) {
+			// the newest picture lives in the alternate buffer: a progressive frame must land on top of it
+			HMRM_CUDA(c, cudaMemcpyAsync(c->d_fb, c->d_fb_alt, (size_t)c->fb_w * (size_t)c->fb_h * 4,
+			                             cudaMemcpyDeviceToDevice, cs));
+		}
 	}
-	rc = enqueue_render(c, f, fb, c->stream, true);
+	if (c->copy_pending[slot]) HMRM_CUDA(c, cudaStreamWaitEvent(cs, c->ev_copied[slot], 0));
+	rc = enqueue_render(c, f, fb, cs, true);
 	if (rc) return rc;
-	HMRM_CUDA(c, cudaEventRecord(c->ev_rendered[slot], c->stream));
+	HMRM_CUDA(c, cudaEventRecord(c->ev_rendered[slot], cs));
 	int rb = f->row_begin, re = f->row_end;
 	if (rb == 0 && re == 0) re = f->screen_height;
 	const size_t row_bytes = (size_t)f->screen_width * 4;
@@ -857,6 +896,7 @@ int hmrm_wait_pending(hmrm_ctx *c, int max_pending) {
 		return HMRM_OK;
 	}
 	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->stream_alt));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	c->copy_pending[0] = c->copy_pending[1] = false;
 	return HMRM_OK;
@@ -877,7 +917,7 @@ int hmrm_get_stats(hmrm_ctx *c, hmrm_stats *out) {
 	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
 	std::memset(out, 0, sizeof *out);
 	DeviceStats ds;
-	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats, sizeof ds, cudaMemcpyDeviceToHost));
+	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats[c->launch_last], sizeof ds, cudaMemcpyDeviceToHost));
 	if (c->last_had_stats) {
 		out->rays = (int64_t)ds.rays;
 		out->box_hits = (int64_t)ds.box_hits;
@@ -889,7 +929,8 @@ int hmrm_get_stats(hmrm_ctx *c, hmrm_stats *out) {
 	out->status = (int32_t)ds.status;
 	if (c->timing_valid) {
 		float ms = 0.f;
-		if (cudaEventElapsedTime(&ms, c->ev_begin, c->ev_end) == cudaSuccess) out->kernel_ms = ms;
+		if (cudaEventElapsedTime(&ms, c->ev_begin[c->launch_last], c->ev_end[c->launch_last]) == cudaSuccess)
+			out->kernel_ms = ms;
 	}
 	return HMRM_OK;
 }
@@ -899,7 +940,7 @@ int hmrm_get_debug_counters(hmrm_ctx *c, int64_t out[12]) {
 	HMRM_CUDA(c, cudaSetDevice(c->device));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
 	DeviceStats ds;
-	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats, sizeof ds, cudaMemcpyDeviceToHost));
+	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats[c->launch_last], sizeof ds, cudaMemcpyDeviceToHost));
 	for (int i = 0; i < 12; ++i) out[i] = (int64_t)ds.dbg[i];
 	return HMRM_OK;
 }
