@@ -33,11 +33,20 @@ std::string g_create_error;
 
 const int kLaunchSlots = 4;
 
-struct Staging {
-	double *host;          // pinned
-	size_t cap;            // doubles
-	cudaEvent_t consumed;  // recorded after the H2D copy that reads `host`
-	bool pending;
+// Everything one launch writes before / while its kernel runs.  A slot is reused only after the kernel that used
+// it last has finished (ev_end), so up to kLaunchSlots frames of one context may be in flight on any streams.
+struct LaunchSlot {
+	DeviceStats *d_stats;
+	unsigned int *d_tile_counter;
+	cudaEvent_t ev_begin, ev_end;
+	bool used;
+	double *sph_host;      // pinned staging of the spherical tables
+	double *d_sph;
+	size_t sph_cap;        // doubles
+	int *d_row_order;
+	int row_cap;
+	double row_key[8];
+	bool row_key_valid;
 };
 
 } // namespace
@@ -70,10 +79,7 @@ struct hmrm_ctx {
 	// per-resolution tables
 	int tab_w, tab_h;
 	std::vector<double> wtab, htab, sph;
-	double *d_wtab, *d_htab, *d_sph[2];   // spherical tables are double-buffered like their staging
-	size_t sph_cap;
-	Staging staging[2];
-	int staging_next;
+	double *d_wtab, *d_htab;
 
 	// outputs
 	uint32_t *d_fb;              // the persistent framebuffer (the reference's framebuf, main/hmap.cpp:612)
@@ -85,15 +91,9 @@ struct hmrm_ctx {
 	int slot;                    // buffer of the most recent hmrm_render_async
 	int32_t *d_step_index;
 	size_t step_index_cap;
-	// tile-row schedule (expensive rows first), cached per view geometry
-	int *d_row_order;
-	int row_order_cap;
-	double row_key[8];
-	bool row_key_valid;
+
 	// per-launch resources, used round-robin so that up to kLaunchSlots kernels of this context may be in flight
-	DeviceStats *d_stats[kLaunchSlots];
-	unsigned int *d_tile_counter[kLaunchSlots];
-	cudaEvent_t ev_begin[kLaunchSlots], ev_end[kLaunchSlots];
+	LaunchSlot slots[kLaunchSlots];
 	int launch_next, launch_last;
 	bool last_had_stats, last_had_step_index, timing_valid;
 	int last_w, last_h;
@@ -141,6 +141,10 @@ int drain(hmrm_ctx *c) {
 	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->stream_alt));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	// kernels launched on the caller's streams (hmrm_render_device) are tracked by their slot's end event
+	for (int i = 0; i < kLaunchSlots; ++i) {
+		if (c->slots[i].used) HMRM_CUDA(c, cudaEventSynchronize(c->slots[i].ev_end));
+	}
 	return HMRM_OK;
 }
 
@@ -205,20 +209,6 @@ int ensure_tables(hmrm_ctx *c, int W, int H) {
 	HMRM_CUDA(c, cudaMalloc(&c->d_htab, (size_t)H * 8));
 	HMRM_CUDA(c, cudaMemcpy(c->d_wtab, c->wtab.data(), (size_t)W * 8, cudaMemcpyHostToDevice));
 	HMRM_CUDA(c, cudaMemcpy(c->d_htab, c->htab.data(), (size_t)H * 8, cudaMemcpyHostToDevice));
-	const size_t need = (size_t)(2 * W + 2 * H);
-	if (need > c->sph_cap) {
-		for (int i = 0; i < 2; ++i) {
-			cudaFree(c->d_sph[i]);
-			c->d_sph[i] = NULL;
-			HMRM_CUDA(c, cudaMalloc(&c->d_sph[i], need * 8));
-			if (c->staging[i].host) cudaFreeHost(c->staging[i].host);
-			c->staging[i].host = NULL;
-			HMRM_CUDA(c, cudaMallocHost(&c->staging[i].host, need * 8));
-			c->staging[i].cap = need;
-			c->staging[i].pending = false;
-		}
-		c->sph_cap = need;
-	}
 	c->tab_w = W;
 	c->tab_h = H;
 	return HMRM_OK;
@@ -284,6 +274,12 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	const int W = f->screen_width, H = f->screen_height;
 	if ((rc = ensure_tables(c, W, H)) != HMRM_OK) return rc;
 
+	// take a launch slot; wait (host side) for the kernel that used it kLaunchSlots launches ago
+	const int ls = c->launch_next;
+	c->launch_next = (ls + 1) % kLaunchSlots;
+	LaunchSlot &slot = c->slots[ls];
+	if (slot.used) HMRM_CUDA(c, cudaEventSynchronize(slot.ev_end));
+
 	const PlaneConst pc = build_plane(*f);
 
 	RenderParams P;
@@ -332,22 +328,24 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	P.htab = c->d_htab;
 
 	if (f->projection == HMRM_SPHERICAL) {
-		const int si = c->staging_next;
-		Staging &st = c->staging[si];
-		c->staging_next ^= 1;
-		if (st.pending) {
-			HMRM_CUDA(c, cudaEventSynchronize(st.consumed));
-			st.pending = false;
+		const size_t need = (size_t)(2 * W + 2 * H);
+		if (need > slot.sph_cap) {
+			if (slot.sph_host) cudaFreeHost(slot.sph_host);
+			cudaFree(slot.d_sph);
+			slot.sph_host = NULL;
+			slot.d_sph = NULL;
+			slot.sph_cap = 0;
+			HMRM_CUDA(c, cudaMallocHost(&slot.sph_host, need * 8));
+			HMRM_CUDA(c, cudaMalloc(&slot.d_sph, need * 8));
+			slot.sph_cap = need;
 		}
 		fill_spherical_tables(pc, W, H, c->wtab, c->htab, &c->sph);
-		std::memcpy(st.host, c->sph.data(), c->sph.size() * 8);
-		HMRM_CUDA(c, cudaMemcpyAsync(c->d_sph[si], st.host, c->sph.size() * 8, cudaMemcpyHostToDevice, stream));
-		HMRM_CUDA(c, cudaEventRecord(st.consumed, stream));
-		st.pending = true;
-		P.cos_ha = c->d_sph[si];
-		P.sin_ha = c->d_sph[si] + W;
-		P.sin_va = c->d_sph[si] + 2 * W;
-		P.cos_va = c->d_sph[si] + 2 * W + H;
+		std::memcpy(slot.sph_host, c->sph.data(), need * 8);
+		HMRM_CUDA(c, cudaMemcpyAsync(slot.d_sph, slot.sph_host, need * 8, cudaMemcpyHostToDevice, stream));
+		P.cos_ha = slot.d_sph;
+		P.sin_ha = slot.d_sph + W;
+		P.sin_va = slot.d_sph + 2 * W;
+		P.cos_va = slot.d_sph + 2 * W + H;
 	}
 
 	// Tile-row schedule: rows whose rays graze the terrain (direction just below the horizon) march for hundreds of
@@ -358,7 +356,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	if (f->projection != HMRM_ORTHOGRAPHIC && P.tiles_y > 1 && !std::getenv("HMRM_NO_ROW_ORDER")) {
 		const double key[8] = {(double)f->projection, (double)W, (double)H, f->vang, f->hfov, (double)row_begin,
 		                       (double)(P.tile_y_first * 65536 + P.tile_y_step), (double)P.tiles_y};
-		if (!c->row_key_valid || std::memcmp(key, c->row_key, sizeof key) != 0) {
+		if (!slot.row_key_valid || std::memcmp(key, slot.row_key, sizeof key) != 0) {
 			std::vector<std::pair<double, int> > cost((size_t)P.tiles_y);
 			for (int t = 0; t < P.tiles_y; ++t) {
 				int py = row_begin + (P.tile_y_first + t * P.tile_y_step) * 4 + 2;
@@ -372,22 +370,21 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 			std::stable_sort(cost.begin(), cost.end());
 			std::vector<int> order((size_t)P.tiles_y);
 			for (int t = 0; t < P.tiles_y; ++t) order[(size_t)t] = cost[(size_t)t].second;
-			if (int rc2 = drain(c)) return rc2;         // a kernel in flight may still read the old schedule
-			if (P.tiles_y > c->row_order_cap) {
-				HMRM_CUDA(c, cudaStreamSynchronize(stream));
-				cudaFree(c->d_row_order);
-				c->d_row_order = NULL;
-				HMRM_CUDA(c, cudaMalloc(&c->d_row_order, (size_t)P.tiles_y * sizeof(int)));
-				c->row_order_cap = P.tiles_y;
+			if (P.tiles_y > slot.row_cap) {
+				cudaFree(slot.d_row_order);
+				slot.d_row_order = NULL;
+				slot.row_cap = 0;
+				HMRM_CUDA(c, cudaMalloc(&slot.d_row_order, (size_t)P.tiles_y * sizeof(int)));
+				slot.row_cap = P.tiles_y;
 			}
-			// the previous schedule may still be read by a kernel in flight on this stream: order the copy after it
-			HMRM_CUDA(c, cudaMemcpyAsync(c->d_row_order, order.data(), (size_t)P.tiles_y * sizeof(int),
+			// pageable source: the copy is staged before the call returns; ordered before this slot's kernel
+			HMRM_CUDA(c, cudaMemcpyAsync(slot.d_row_order, order.data(), (size_t)P.tiles_y * sizeof(int),
 			                             cudaMemcpyHostToDevice, stream));
 			HMRM_CUDA(c, cudaStreamSynchronize(stream));
-			std::memcpy(c->row_key, key, sizeof key);
-			c->row_key_valid = true;
+			std::memcpy(slot.row_key, key, sizeof key);
+			slot.row_key_valid = true;
 		}
-		P.row_order = c->d_row_order;
+		P.row_order = slot.d_row_order;
 	}
 
 	// FP32 miss prefilter (see ray_setup.cuh:fast_miss): the box inflated by 2^-12 of the scene scale
@@ -435,13 +432,11 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		HMRM_CUDA(c, cudaMemsetAsync(c->d_step_index, 0xFD, need * 4, stream));   // -3 = not rendered... bytes FD
 		P.step_index = c->d_step_index;
 	}
-	const int ls = c->launch_next;
-	c->launch_next = (ls + 1) % kLaunchSlots;
-	P.stats = c->d_stats[ls];
-	P.tile_counter = c->d_tile_counter[ls];
+	P.stats = slot.d_stats;
+	P.tile_counter = slot.d_tile_counter;
 
-	HMRM_CUDA(c, cudaMemsetAsync(c->d_tile_counter[ls], 0, sizeof(unsigned int), stream));
-	HMRM_CUDA(c, cudaMemsetAsync(c->d_stats[ls], 0, sizeof(DeviceStats), stream));
+	HMRM_CUDA(c, cudaMemsetAsync(slot.d_tile_counter, 0, sizeof(unsigned int), stream));
+	HMRM_CUDA(c, cudaMemsetAsync(slot.d_stats, 0, sizeof(DeviceStats), stream));
 
 	int traversal = f->traversal;
 	if (traversal == HMRM_TRAVERSAL_AUTO) traversal = c->skip_ready ? HMRM_TRAVERSAL_SKIP : HMRM_TRAVERSAL_BRUTE;
@@ -488,7 +483,8 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	if (blocks > max_useful) blocks = max_useful;
 	if (blocks < 1) blocks = 1;
 
-	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_begin[ls], stream));
+	(void)timed;
+	HMRM_CUDA(c, cudaEventRecord(slot.ev_begin, stream));
 	if (traversal == HMRM_TRAVERSAL_SKIP) {
 		const bool stats_kernel = want_stats || want_steps;
 		if (P.fast_setup) {
@@ -505,7 +501,8 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		else k2_render_brute<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
 	}
 	HMRM_CUDA(c, cudaGetLastError());
-	if (timed) HMRM_CUDA(c, cudaEventRecord(c->ev_end[ls], stream));
+	HMRM_CUDA(c, cudaEventRecord(slot.ev_end, stream));
+	slot.used = true;
 	c->launch_last = ls;
 
 	c->last_stream = stream;
@@ -573,15 +570,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->skip_ready = false;
 	c->tab_w = c->tab_h = 0;
 	c->d_wtab = c->d_htab = NULL;
-	c->d_sph[0] = c->d_sph[1] = NULL;
-	c->sph_cap = 0;
-	for (int i = 0; i < 2; ++i) {
-		c->staging[i].host = NULL;
-		c->staging[i].cap = 0;
-		c->staging[i].pending = false;
-		c->staging[i].consumed = NULL;
-	}
-	c->staging_next = 0;
+	std::memset(c->slots, 0, sizeof c->slots);
 	c->d_fb = c->d_fb_alt = NULL;
 	c->fb_w = c->fb_h = 0;
 	c->copy_stream = NULL;
@@ -590,14 +579,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->slot = 0;
 	c->d_step_index = NULL;
 	c->step_index_cap = 0;
-	c->d_row_order = NULL;
-	c->row_order_cap = 0;
-	c->row_key_valid = false;
-	for (int i = 0; i < kLaunchSlots; ++i) {
-		c->d_stats[i] = NULL;
-		c->d_tile_counter[i] = NULL;
-		c->ev_begin[i] = c->ev_end[i] = NULL;
-	}
+
 	c->launch_next = c->launch_last = 0;
 	c->last_had_stats = c->last_had_step_index = c->timing_valid = false;
 	c->last_w = c->last_h = 0;
@@ -611,13 +593,11 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	}
 	if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->stream_alt, cudaStreamNonBlocking);
 	for (int i = 0; i < kLaunchSlots && err == cudaSuccess; ++i) {
-		err = cudaEventCreate(&c->ev_begin[i]);
-		if (err == cudaSuccess) err = cudaEventCreate(&c->ev_end[i]);
-		if (err == cudaSuccess) err = cudaMalloc(&c->d_stats[i], sizeof(DeviceStats));
-		if (err == cudaSuccess) err = cudaMalloc(&c->d_tile_counter[i], 256);
+		err = cudaEventCreate(&c->slots[i].ev_begin);
+		if (err == cudaSuccess) err = cudaEventCreate(&c->slots[i].ev_end);
+		if (err == cudaSuccess) err = cudaMalloc(&c->slots[i].d_stats, sizeof(DeviceStats));
+		if (err == cudaSuccess) err = cudaMalloc(&c->slots[i].d_tile_counter, 256);
 	}
-	for (int i = 0; i < 2 && err == cudaSuccess; ++i)
-		err = cudaEventCreateWithFlags(&c->staging[i].consumed, cudaEventDisableTiming);
 	if (err == cudaSuccess) err = cudaMalloc(&c->d_max_bits, 32);
 	if (err != cudaSuccess) {
 		fail(NULL, HMRM_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));
@@ -637,11 +617,7 @@ void hmrm_destroy(hmrm_ctx *c) {
 	cudaFree(c->d_max_bits);
 	cudaFree(c->d_wtab);
 	cudaFree(c->d_htab);
-	for (int i = 0; i < 2; ++i) {
-		cudaFree(c->d_sph[i]);
-		if (c->staging[i].host) cudaFreeHost(c->staging[i].host);
-		if (c->staging[i].consumed) cudaEventDestroy(c->staging[i].consumed);
-	}
+
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	cudaFree(c->d_fb);
 	cudaFree(c->d_fb_alt);
@@ -651,12 +627,15 @@ void hmrm_destroy(hmrm_ctx *c) {
 	}
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	cudaFree(c->d_step_index);
-	cudaFree(c->d_row_order);
 	for (int i = 0; i < kLaunchSlots; ++i) {
-		cudaFree(c->d_stats[i]);
-		cudaFree(c->d_tile_counter[i]);
-		if (c->ev_begin[i]) cudaEventDestroy(c->ev_begin[i]);
-		if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
+		LaunchSlot &sl = c->slots[i];
+		cudaFree(sl.d_stats);
+		cudaFree(sl.d_tile_counter);
+		cudaFree(sl.d_sph);
+		cudaFree(sl.d_row_order);
+		if (sl.sph_host) cudaFreeHost(sl.sph_host);
+		if (sl.ev_begin) cudaEventDestroy(sl.ev_begin);
+		if (sl.ev_end) cudaEventDestroy(sl.ev_end);
 	}
 	if (c->stream) cudaStreamDestroy(c->stream);
 	if (c->stream_alt) cudaStreamDestroy(c->stream_alt);
@@ -917,7 +896,7 @@ int hmrm_get_stats(hmrm_ctx *c, hmrm_stats *out) {
 	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
 	std::memset(out, 0, sizeof *out);
 	DeviceStats ds;
-	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats[c->launch_last], sizeof ds, cudaMemcpyDeviceToHost));
+	HMRM_CUDA(c, cudaMemcpy(&ds, c->slots[c->launch_last].d_stats, sizeof ds, cudaMemcpyDeviceToHost));
 	if (c->last_had_stats) {
 		out->rays = (int64_t)ds.rays;
 		out->box_hits = (int64_t)ds.box_hits;
@@ -929,7 +908,7 @@ int hmrm_get_stats(hmrm_ctx *c, hmrm_stats *out) {
 	out->status = (int32_t)ds.status;
 	if (c->timing_valid) {
 		float ms = 0.f;
-		if (cudaEventElapsedTime(&ms, c->ev_begin[c->launch_last], c->ev_end[c->launch_last]) == cudaSuccess)
+		if (cudaEventElapsedTime(&ms, c->slots[c->launch_last].ev_begin, c->slots[c->launch_last].ev_end) == cudaSuccess)
 			out->kernel_ms = ms;
 	}
 	return HMRM_OK;
@@ -940,7 +919,7 @@ int hmrm_get_debug_counters(hmrm_ctx *c, int64_t out[12]) {
 	HMRM_CUDA(c, cudaSetDevice(c->device));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
 	DeviceStats ds;
-	HMRM_CUDA(c, cudaMemcpy(&ds, c->d_stats[c->launch_last], sizeof ds, cudaMemcpyDeviceToHost));
+	HMRM_CUDA(c, cudaMemcpy(&ds, c->slots[c->launch_last].d_stats, sizeof ds, cudaMemcpyDeviceToHost));
 	for (int i = 0; i < 12; ++i) out[i] = (int64_t)ds.dbg[i];
 	return HMRM_OK;
 }
