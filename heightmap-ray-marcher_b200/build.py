@@ -64,6 +64,17 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_hmap_fake_sdl(shim_dir: Path, fake_sdl_obj: Path, out: Path) -> Path:
+    """Interactive `hmap` (-DHMAP_WITH_SDL) linked against a scripted fake SDL: test builds only (the shim and
+    the object live with the test oracle; SDL2 itself is not installable in this image)."""
+    srcs = sorted(HOST.glob("*.cpp"))
+    cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-ffp-contract=off", "-DHMAP_WITH_SDL", "-I", str(shim_dir),
+           "-o", str(out), *[str(s) for s in srcs], str(fake_sdl_obj), "-L", str(PKG), "-lhmrm", "-lz", "-pthread",
+           f"-Wl,-rpath,{PKG}"]
+    subprocess.run(cmd, check=True, cwd=str(PKG))
+    return out
+
+
 if __name__ == "__main__":
     build_lib(force="--force" in sys.argv, verbose=True)
     build_hmap(force="--force" in sys.argv)

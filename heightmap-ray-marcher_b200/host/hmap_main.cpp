@@ -31,6 +31,12 @@
 
 using namespace hmrm_host;
 
+#ifdef HMAP_WITH_SDL
+namespace hmrm_host {
+int run_interactive(Config &cfg, hmrm_ctx *ctx, int precision, int traversal);   // hmap_sdl.cpp
+}
+#endif
+
 namespace {
 
 struct Options {
@@ -204,11 +210,13 @@ int main(int argc, char **argv) {
 	input.close();
 	if (opt.parse_only) return 0;
 
+#ifndef HMAP_WITH_SDL
 	if (opt.headless_out.empty() && opt.script_path.empty()) {
 		std::cerr << "hmap: this build has no SDL window (SDL2 is not available here); use --headless out.png "
 		             "or --script frames.txt\n";
 		return 1;
 	}
+#endif
 
 	const int available = hmrm_device_count();
 	if (available < 1) {
@@ -225,6 +233,16 @@ int main(int argc, char **argv) {
 	}
 	cfg.maps_changed = true;
 	push_maps(devs, cfg);
+
+#ifdef HMAP_WITH_SDL
+	if (opt.headless_out.empty() && opt.script_path.empty()) {
+		// the reference's interactive mode: `hmap config.txt`
+		if (opt.projection) cfg.image_plane = opt.projection;
+		const int rc = run_interactive(cfg, devs[0].ctx, opt.precision, opt.traversal);
+		for (size_t i = 0; i < devs.size(); ++i) hmrm_destroy(devs[i].ctx);
+		return rc;
+	}
+#endif
 
 	Totals totals;
 	const std::clock_t t_start = std::clock();

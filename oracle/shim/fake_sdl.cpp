@@ -21,6 +21,12 @@
 //                             computed before events are drained (:661-672 vs
 //                             :687), every scripted state is rendered twice and
 //                             only the second render is recorded.
+//   HMRM_FAKE_EVENTS  path    general event script, one event per line "<iteration> <kind> <args>":
+//                               key <1|2|3|q|r|backquote|backspace|return|f1|f11|f12> [ctrl] [shift]   (SDL_KEYUP)
+//                               text <string>          (SDL_TEXTINPUT)      motion <xrel> <yrel>      wheel <y>
+//                               hold <w|a|s|d|q|space> <0|1>  (keyboard state from that iteration on)
+//                               resize <w> <h>         (SDL_WINDOWEVENT_SIZE_CHANGED)           quit
+//                             every iteration up to HMRM_FAKE_FRAMES is recorded.
 #include <SDL2/SDL.h>
 #include <SDL2/SDL_ttf.h>
 
@@ -30,6 +36,7 @@
 #include <cstring>
 #include <deque>
 #include <fstream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -49,13 +56,22 @@ struct FakeState {
 	int filled_iter;
 	int recorded;
 	std::deque<SDL_Event> queue;
+	std::deque<int> queue_mod;          // modifier state while the matching event is being handled
+	int current_mod;
+	int win_w, win_h;
+	struct Scripted {
+		int iter;
+		std::string kind;
+		std::vector<std::string> args;
+	};
+	std::vector<Scripted> events;
 	Uint8 keys[SDL_NUM_SCANCODES];
 	std::chrono::steady_clock::time_point t_mod;
 	bool init_done;
 
 	FakeState()
 		: proj(1), frames(1), warmup(0), scripted(false), tex_w(0), tex_h(0),
-		  ticks_calls(0), filled_iter(-1), recorded(0), init_done(false) {
+		  ticks_calls(0), filled_iter(-1), recorded(0), current_mod(0), win_w(0), win_h(0), init_done(false) {
 		std::memset(keys, 0, sizeof keys);
 	}
 };
@@ -84,14 +100,119 @@ void lazy_init() {
 		g.scripted = true;
 		g.frames = (int)g.script.size();
 	}
+	if (const char *v = std::getenv("HMRM_FAKE_EVENTS")) {
+		std::ifstream in(v);
+		std::string line;
+		while (std::getline(in, line)) {
+			std::istringstream ss(line);
+			FakeState::Scripted ev;
+			if (!(ss >> ev.iter >> ev.kind)) continue;
+			if (ev.kind == "text") {
+				std::string rest;
+				std::getline(ss, rest);
+				if (!rest.empty() && rest[0] == ' ') rest.erase(0, 1);
+				ev.args.push_back(rest);
+			}
+			else {
+				std::string a;
+				while (ss >> a) ev.args.push_back(a);
+			}
+			g.events.push_back(ev);
+		}
+	}
 }
+
+void push_event(const SDL_Event &e, int mod) {
+	g.queue.push_back(e);
+	g.queue_mod.push_back(mod);
+}
+
+SDL_Keycode key_by_name(const std::string &n) {
+	if (n == "1") return SDLK_1;
+	if (n == "2") return SDLK_2;
+	if (n == "3") return SDLK_3;
+	if (n == "q") return SDLK_q;
+	if (n == "r") return SDLK_r;
+	if (n == "backquote") return SDLK_BACKQUOTE;
+	if (n == "backspace") return SDLK_BACKSPACE;
+	if (n == "return") return SDLK_RETURN;
+	if (n == "f1") return SDLK_F1;
+	if (n == "f11") return SDLK_F11;
+	if (n == "f12") return SDLK_F12;
+	return 0;
+}
+
+int scancode_by_name(const std::string &n) {
+	if (n == "w") return SDL_SCANCODE_W;
+	if (n == "a") return SDL_SCANCODE_A;
+	if (n == "s") return SDL_SCANCODE_S;
+	if (n == "d") return SDL_SCANCODE_D;
+	if (n == "q") return SDL_SCANCODE_Q;
+	if (n == "space") return SDL_SCANCODE_SPACE;
+	return 0;
+}
+
+void fill_scripted_events(int it) {
+	for (size_t i = 0; i < g.events.size(); ++i) {
+		const FakeState::Scripted &s = g.events[i];
+		if (s.iter != it) continue;
+		SDL_Event e;
+		std::memset(&e, 0, sizeof e);
+		if (s.kind == "key" && !s.args.empty()) {
+			int mod = KMOD_NONE;
+			for (size_t a = 1; a < s.args.size(); ++a) {
+				if (s.args[a] == "ctrl") mod |= KMOD_LCTRL;
+				if (s.args[a] == "shift") mod |= KMOD_LSHIFT;
+			}
+			e.type = SDL_KEYUP;
+			e.key.keysym.sym = key_by_name(s.args[0]);
+			push_event(e, mod);
+		}
+		else if (s.kind == "text" && !s.args.empty()) {
+			for (size_t p = 0; p < s.args[0].size(); p += 31) {
+				std::memset(&e, 0, sizeof e);
+				e.type = SDL_TEXTINPUT;
+				const std::string chunk = s.args[0].substr(p, 31);
+				std::memcpy(e.text.text, chunk.c_str(), chunk.size());
+				push_event(e, KMOD_NONE);
+			}
+		}
+		else if (s.kind == "motion" && s.args.size() >= 2) {
+			e.type = SDL_MOUSEMOTION;
+			e.motion.xrel = std::atoi(s.args[0].c_str());
+			e.motion.yrel = std::atoi(s.args[1].c_str());
+			push_event(e, KMOD_NONE);
+		}
+		else if (s.kind == "wheel" && !s.args.empty()) {
+			e.type = SDL_MOUSEWHEEL;
+			e.wheel.y = std::atoi(s.args[0].c_str());
+			push_event(e, KMOD_NONE);
+		}
+		else if (s.kind == "hold" && s.args.size() >= 2) {
+			g.keys[scancode_by_name(s.args[0])] = (Uint8)std::atoi(s.args[1].c_str());
+		}
+		else if (s.kind == "resize" && s.args.size() >= 2) {
+			g.win_w = std::atoi(s.args[0].c_str());
+			g.win_h = std::atoi(s.args[1].c_str());
+			e.type = SDL_WINDOWEVENT;
+			e.window.event = SDL_WINDOWEVENT_SIZE_CHANGED;
+			push_event(e, KMOD_NONE);
+		}
+		else if (s.kind == "quit") {
+			e.type = SDL_QUIT;
+			push_event(e, KMOD_NONE);
+		}
+	}
+}
+
+void push_event(const SDL_Event &e, int mod);
 
 void push_key(SDL_Keycode sym) {
 	SDL_Event e;
 	std::memset(&e, 0, sizeof e);
 	e.type = SDL_KEYUP;
 	e.key.keysym.sym = sym;
-	g.queue.push_back(e);
+	push_event(e, KMOD_NONE);
 }
 
 void push_text(const std::string &s) {
@@ -101,9 +222,11 @@ void push_text(const std::string &s) {
 		e.type = SDL_TEXTINPUT;
 		std::string chunk = s.substr(i, 31);
 		std::memcpy(e.text.text, chunk.c_str(), chunk.size());
-		g.queue.push_back(e);
+		push_event(e, KMOD_NONE);
 	}
 }
+
+void fill_scripted_events(int it);
 
 int iteration() { return g.ticks_calls - 2; }
 
@@ -131,11 +254,12 @@ void fill_events(int it) {
 		push_text(g.script[(size_t)(it / 2)]);
 		push_key(SDLK_RETURN);
 	}
+	fill_scripted_events(it);
 	if (it > last_iteration()) {
 		SDL_Event e;
 		std::memset(&e, 0, sizeof e);
 		e.type = SDL_QUIT;
-		g.queue.push_back(e);
+		push_event(e, KMOD_NONE);
 	}
 }
 
@@ -155,8 +279,8 @@ SDL_Window *SDL_CreateWindow(const char *, int, int, int, int, Uint32) {
 void SDL_DestroyWindow(SDL_Window *) {}
 void SDL_SetWindowSize(SDL_Window *, int, int) {}
 void SDL_GetWindowSize(SDL_Window *, int *w, int *h) {
-	if (w) *w = g.tex_w;
-	if (h) *h = g.tex_h;
+	if (w) *w = g.win_w ? g.win_w : g.tex_w;
+	if (h) *h = g.win_h ? g.win_h : g.tex_h;
 }
 int SDL_SetWindowFullscreen(SDL_Window *, Uint32) { return 0; }
 
@@ -225,9 +349,14 @@ int SDL_PollEvent(SDL_Event *event) {
 		g.filled_iter = it;
 		fill_events(it);
 	}
-	if (g.queue.empty()) return 0;
+	if (g.queue.empty()) {
+		g.current_mod = KMOD_NONE;
+		return 0;
+	}
 	if (event) *event = g.queue.front();
+	g.current_mod = g.queue_mod.front();
 	g.queue.pop_front();
+	g.queue_mod.pop_front();
 	return 1;
 }
 
@@ -238,7 +367,7 @@ const Uint8 *SDL_GetKeyboardState(int *numkeys) {
 
 SDL_Keymod SDL_GetModState(void) {
 	g.t_mod = std::chrono::steady_clock::now();
-	return KMOD_NONE;
+	return (SDL_Keymod)g.current_mod;
 }
 
 int SDL_SetRelativeMouseMode(SDL_bool) { return 0; }
