@@ -309,17 +309,18 @@ def ours_arm(args, wl) -> None:
         # K frames, device-resident, two frames in flight: frames alternate between two streams (and two output
         # buffers) so that the next frame's CTAs fill the SMs that the previous frame's tail leaves idle.  The timed
         # region starts on `stream` with both streams idle and ends on `stream` after it has joined `stream2`.
-        stream2 = torch.cuda.Stream(device=local)
-        d_out2 = torch.zeros_like(d_out)
-        stream2.wait_stream(stream)
+        n_flight = max(1, min(4, args.inflight))
+        streams = [stream] + [torch.cuda.Stream(device=local) for _ in range(n_flight - 1)]
+        outs = [d_out] + [torch.zeros_like(d_out) for _ in range(n_flight - 1)]
+        for s2 in streams[1:]:
+            s2.wait_stream(stream)
         ev0.record(stream)
-        stream2.wait_event(ev0)
+        for s2 in streams[1:]:
+            s2.wait_event(ev0)
         for i, n in enumerate(my_frames):
-            if i & 1:
-                r.render_device(frame_of(n), d_out2, stream2.cuda_stream)
-            else:
-                r.render_device(frame_of(n), d_out, stream.cuda_stream)
-        stream.wait_stream(stream2)
+            r.render_device(frame_of(n), outs[i % n_flight], streams[i % n_flight].cuda_stream)
+        for s2 in streams[1:]:
+            stream.wait_stream(s2)
         ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
@@ -421,7 +422,8 @@ def ours_arm(args, wl) -> None:
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "desc": wl["desc"], "traversal": args.traversal,
                        "precision": "fp64_exact",
-                       "in_flight": "1 frame" if bands else "2 frames on 2 streams (tail of frame n overlaps head of n+1)",
+                       "in_flight": "1 frame" if bands else f"{max(1, min(4, args.inflight))} frames on as many streams "
+                                    "(the tail of frame n overlaps the head of frame n+1)",
                        "sharding": (f"each frame split into interleaved 4-row tile bands over {world} GPU(s), RGBA8 bands "
                                     "gathered to rank 0 (NCCL), maps replicated") if bands else
                                    f"frames round-robin over {world} GPU(s), maps replicated, no collective",
@@ -476,6 +478,7 @@ def main() -> None:
     ap.add_argument("--traversal", choices=["auto", "brute", "skip"], default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=2)
+    ap.add_argument("--inflight", type=int, default=2, help="frames in flight in the device-resident timing (1..4)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
