@@ -22,6 +22,7 @@ from .binding import (  # noqa: F401
     TRAVERSAL_AUTO,
     TRAVERSAL_BRUTE,
     TRAVERSAL_SKIP,
+    TRAVERSAL_SKIP_FP64,
     Frame,
     HmrmError,
     Renderer,

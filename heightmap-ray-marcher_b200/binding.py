@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 
 PERSPECTIVE, SPHERICAL, ORTHOGRAPHIC = 1, 2, 3          # main/hmap.cpp:104-106
 FP64_EXACT, FP32_FAST = 0, 1
-TRAVERSAL_AUTO, TRAVERSAL_BRUTE, TRAVERSAL_SKIP = 0, 1, 2
+TRAVERSAL_AUTO, TRAVERSAL_BRUTE, TRAVERSAL_SKIP, TRAVERSAL_SKIP_FP64 = 0, 1, 2, 3
 FLAG_STATS, FLAG_STEP_INDEX = 1, 2
 
 

@@ -22,6 +22,7 @@
 #include "k1_prepass.cuh"
 #include "k2_render_brute.cuh"
 #include "k2_render_skip.cuh"
+#include "k2_render_lin.cuh"
 #include "render_params.h"
 #include "synth_fbm.h"
 
@@ -440,9 +441,9 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 
 	int traversal = f->traversal;
 	if (traversal == HMRM_TRAVERSAL_AUTO) traversal = c->skip_ready ? HMRM_TRAVERSAL_SKIP : HMRM_TRAVERSAL_BRUTE;
-	if (traversal != HMRM_TRAVERSAL_BRUTE && traversal != HMRM_TRAVERSAL_SKIP)
+	if (traversal != HMRM_TRAVERSAL_BRUTE && traversal != HMRM_TRAVERSAL_SKIP && traversal != HMRM_TRAVERSAL_SKIP_FP64)
 		return fail(c, HMRM_ERR_INVALID, "unknown traversal %d", f->traversal);
-	if (traversal == HMRM_TRAVERSAL_SKIP) {
+	if (traversal != HMRM_TRAVERSAL_BRUTE) {
 		if (!c->skip_ready)
 			return fail(c, HMRM_ERR_STATE, "the height range could not be quantised; use HMRM_TRAVERSAL_BRUTE");
 		int dim = c->map_w > c->map_h ? c->map_w : c->map_h, clog = 0;
@@ -486,6 +487,17 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	(void)timed;
 	HMRM_CUDA(c, cudaEventRecord(slot.ev_begin, stream));
 	if (traversal == HMRM_TRAVERSAL_SKIP) {
+		const bool stats_kernel = want_stats || want_steps;
+		if (P.fast_setup) {
+			if (stats_kernel) k2_render_lin<true, true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+			else k2_render_lin<false, true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		}
+		else {
+			if (stats_kernel) k2_render_lin<true, false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+			else k2_render_lin<false, false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		}
+	}
+	else if (traversal == HMRM_TRAVERSAL_SKIP_FP64) {
 		const bool stats_kernel = want_stats || want_steps;
 		if (P.fast_setup) {
 			if (stats_kernel) k2_render_skip<true, true><<<blocks, warps_per_block * 32, 0, stream>>>(P);

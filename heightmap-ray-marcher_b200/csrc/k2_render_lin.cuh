@@ -1,0 +1,352 @@
+// K2 (linear-model skip traversal) — production kernel of the exact mode.
+//
+// Same contract as k2_render_brute.cuh (main/hmap.cpp:978-1058): same framebuffer, same per-pixel first-hit
+// sample index, same reference-equivalent step count.  It builds on the three facts of k2_render_skip.cuh
+// (closed-form stepping, monotone fixed point, monotone rays + dilated maxima) and adds a fourth that removes
+// FP64 — and every divide, refusal and binade check — from the hot loop:
+//
+// (4) Linear integer model with a proven error bound.  Let P_j be the reference's j-th sample (P_0 exact,
+//     P_{j+1} = fl(P_j + s) per axis) and X(x) = x * 2^k / gw its position in fixed-point units (2^-k cells; the
+//     height axis uses Zq units).  The kernel tracks   V_j = V_0 + round(j * D / 2^16)   in integers, with
+//     V_0 = round(X(P_0)) (one DFMA, |err| <= 0.5 + 2^-22) and D = round(X(s) * 2^16) (|err| <= 0.5 + tiny), so
+//       |V_j - X(P_0 + j s)| <= 0.5 + j * 2^-17 + 0.5            (V_0, slope quantisation, final rounding)
+//       |X(P_j) - X(P_0 + j s)| <= j * 2^-53 * max|X| <= j * 2^-22   (accumulated FP64 rounding of the adds)
+//     and with j < 2^16 between exact re-anchors:   |V_j - X(P_j)| < 1.6 units  (and the reference's rounded
+//     quotient fl(x/gw) differs from x/gw by < 2^-22 units).  Everything the march decides is therefore decided
+//     from V_j with a margin of HMRM_LIN_MARGIN = 4 units:
+//       * cell index   = V >> k            when V is >= 4 units away from a cell edge,
+//       * inside grid / outside grid       when V is >= 4 units away from the grid edge (the low edge is at -1 cell:
+//                                          (int) truncates toward zero, so (-1, 0) still is cell 0),
+//       * above the (dilated) block max q  when Z_j - 4 > q  (q < 65535: clamped values never prove anything),
+//       * hit                              when Z_j + 4 < q  (q > 0; same monotone Zq16 argument as k2_render_skip.cuh),
+//       * a jump of m samples              when samples n and n+m are both >= 4 units inside the cleared
+//                                          neighbourhood and the grid, and both have Z - 4 > q: V is monotone in j.
+//     Any sample that is NOT decided with that margin is handed to resolve_exact(): the exact FP64 position P_n is
+//     reconstructed from the last exact anchor with the binade-aware closed form (fact 1) and the reference's own
+//     expressions (divide, truncate, compare with the FP64 surface) decide it.  On the bench frame that happens
+//     for a few percent of the rays, once.
+//
+// Rays whose per-step motion or start position does not fit the integer model (steps of thousands of cells, a
+// start 2^31 units away, NaNs, no lateral motion at all) take the plain per-step loop of the brute kernel.
+#ifndef HMRM_K2_RENDER_LIN_CUH
+#define HMRM_K2_RENDER_LIN_CUH
+
+#include "k2_render_skip.cuh"
+
+namespace hmrm {
+
+#define HMRM_LIN_FRAC 16
+#define HMRM_LIN_PERIOD 65536u      // samples between exact re-anchors (keeps the error bound of fact 4)
+#define HMRM_LIN_MARGIN 4
+
+// Move the exact anchor (sample index a, position in ax/ay/az.p) forward to sample n.  Exact: closed form inside
+// binades (end point checked), plain adds across them.
+__device__ __noinline__ void advance_exact(AxisState &ax, AxisState &ay, AxisState &az, unsigned &a, unsigned n) {
+	while (a < n) {
+		unsigned m = n - a;
+		bool jumped = false;
+		if (m >= 2u) {
+			axis_refresh(ax);
+			axis_refresh(ay);
+			axis_refresh(az);
+			if (ax.tag != INT_MIN && ay.tag != INT_MIN && az.tag != INT_MIN) {
+				int lim = (int)min(m, (unsigned)HMRM_JUMP_CAP);
+				lim = min(lim, steps_to_binade_edge(ax));
+				lim = min(lim, steps_to_binade_edge(ay));
+				lim = min(lim, steps_to_binade_edge(az));
+				// the edge distances are estimates: verify, and back off a little if the estimate was too long
+				for (int tries = 0; lim >= 2 && tries < 3; ++tries) {
+					const double md = small_int_to_double(lim);
+					const double nx = __fma_rn(md, ax.S, ax.p), ny = __fma_rn(md, ay.S, ay.p), nz = __fma_rn(md, az.S, az.p);
+					if (binade_tag(nx) == ax.tag && binade_tag(ny) == ay.tag && binade_tag(nz) == az.tag) {
+						ax.p = nx; ay.p = ny; az.p = nz;
+						a += (unsigned)lim;
+						jumped = true;
+						break;
+					}
+					lim -= 1 + (lim >> 4);
+				}
+			}
+		}
+		if (!jumped) {
+			ax.p = fadd(ax.p, ax.s);
+			ay.p = fadd(ay.p, ay.s);
+			az.p = fadd(az.p, az.s);
+			a += 1u;
+		}
+	}
+}
+
+struct LinAxis {
+	long long d;     // per-step motion in units * 2^16
+	int v0;          // position of the base sample in units
+};
+
+__device__ __forceinline__ long long lin_at(const LinAxis &l, unsigned j) {
+	return (long long)l.v0 + (((long long)j * l.d + (1LL << (HMRM_LIN_FRAC - 1))) >> HMRM_LIN_FRAC);
+}
+
+// slope of one axis of the integer model; false if it does not fit (|motion| >= 2^26 units per step, NaN)
+__device__ __forceinline__ bool lin_slope(double s_units, long long &d) {
+	if (!(fabs(s_units) < 67108864.0)) return false;
+	d = __double2ll_rn(s_units * 65536.0);
+	return true;
+}
+
+template <bool kStats>
+__device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray, double ex, double ey, double ez,
+                                          uint32_t &rgba, bool &real_hit, int &first_hit, PixelTally &tally) {
+	const int k = P.fx_bits;
+	// exact state: the anchor sample and the reference's per-step addend
+	AxisState ax, ay, az;
+	ax.p = fadd(ex, fmul(P.nudge, ray.dx));           // main/hmap.cpp:998
+	ay.p = fadd(ey, fmul(P.nudge, ray.dy));
+	az.p = fadd(ez, fmul(P.nudge, ray.dz));
+	ax.s = fmul(P.step_dist, ray.dx);                  // :1037
+	ay.s = fmul(P.step_dist, ray.dy);
+	az.s = fmul(P.step_dist, ray.dz);
+	ax.tag = ay.tag = az.tag = INT_MIN;
+	ax.S = ay.S = az.S = 0.0;
+	unsigned anchor = 0u;     // sample index of (ax.p, ay.p, az.p)
+
+	unsigned n = 0u;          // sample under examination
+	unsigned fetches = 0u;
+
+	// ---- integer model of this ray ----
+	LinAxis lx, ly, lz;
+	bool model = lin_slope(ax.s * P.fx_scale, lx.d) && lin_slope(-ay.s * P.fx_scale, ly.d) && lin_slope(az.s * P.zq_scale, lz.d);
+	// no lateral motion and not coming down: such a ray can only end by the reference's hang; the per-step loop cuts it
+	model = model && (lx.d != 0 || ly.d != 0 || lz.d < 0);
+	auto rebase = [&]() -> bool {                     // V_0 of the model := the exact anchor
+		int vx, vy, vz;
+		const bool okx = magic_decode(__fma_rn(ax.p, P.fx_scale, HMRM_MAGIC), vx);
+		const bool oky = magic_decode(__fma_rn(ay.p, -P.fx_scale, HMRM_MAGIC), vy);
+		const bool okz = magic_decode(__fma_rn(az.p, P.zq_scale, P.zq_offset), vz);
+		lx.v0 = vx; ly.v0 = vy; lz.v0 = vz;
+		return okx && oky && okz;
+	};
+	unsigned base = 0u;       // sample index of V_0
+	model = model && rebase();
+
+	bool finished = false;     // the integer-model loop reached a verdict
+	if (model) {
+	const float inv_adx = fast_rcp(fabsf((float)lx.d) * (1.0f / 65536.0f));
+	const float inv_ady = fast_rcp(fabsf((float)ly.d) * (1.0f / 65536.0f));
+	const float adz = fabsf((float)lz.d) * (1.0f / 65536.0f);
+	const float inv_adz = fast_rcp(adz);
+	const int cell_exit = (int)fminf(P.cell_exit_scale * adz + 32.0f, 1.0e9f);
+	const long long grid_vx = (long long)P.map_w << k, grid_vy = (long long)P.map_h << k;   // <= 2^30
+	const int cell_mask = (1 << k) - 1;
+	int level = P.lstart;
+
+	auto probe = [&](int lvl, int vx, int vy) -> int {
+		const uint2 d = P.lv_desc[lvl];
+		const unsigned idx = d.x + (unsigned)(vy >> (k + lvl)) * d.y + (unsigned)(vx >> (k + lvl));
+		return (int)__ldg(P.lv + idx);
+	};
+
+	for (;;) {
+		// keep the error bound: re-anchor the model on an exact position every HMRM_LIN_PERIOD samples
+		if (n - base >= HMRM_LIN_PERIOD) {
+			advance_exact(ax, ay, az, anchor, n);
+			base = n;
+			if (!rebase()) {                 // left the representable range: finish with the per-step loop below
+				model = false;
+				break;
+			}
+		}
+		const unsigned j = n - base;
+		const long long wx = lin_at(lx, j), wy = lin_at(ly, j);
+		// Certainly outside the grid (main/hmap.cpp:1006-1011)?  The reference truncates toward zero (:1001-1004), so
+		// coordinates in (-1, 0) cells still map to cell 0: the low edge of the grid is at -1 cell, not at 0.
+		const long long low_edge = -(1LL << k) - HMRM_LIN_MARGIN;
+		if (wx < low_edge || wy < low_edge || wx >= grid_vx + HMRM_LIN_MARGIN || wy >= grid_vy + HMRM_LIN_MARGIN) {
+			finished = true;
+			break;
+		}
+		const int vx = (int)wx, vy = (int)wy;
+		long long wz = lin_at(lz, j);
+		wz = wz < -1073741824LL ? -1073741824LL : (wz > 1073741824LL ? 1073741824LL : wz);
+		const int vz = (int)wz;
+
+		// does this sample need the exact treatment?  (within the margin of the grid edge; at level 0 also of a cell edge)
+		// (everything below +4 units, i.e. the whole (-1, 0] strip of the truncation quirk, goes the exact way too)
+		bool exact = vx < HMRM_LIN_MARGIN || vy < HMRM_LIN_MARGIN || wx >= grid_vx - HMRM_LIN_MARGIN || wy >= grid_vy - HMRM_LIN_MARGIN;
+		int q = 0;
+		if (!exact) {
+			// ---- A: find a level whose neighbourhood this sample clears (descend), or reach the cell itself ----
+			q = probe(level, vx, vy);
+			if (kStats) fetches += 1u;
+			while (!(vz - HMRM_LIN_MARGIN > q && q < 65535) && level > 0) {
+				level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
+				q = probe(level, vx, vy);
+				if (kStats) { fetches += 1u; tally.dbg[3] += 1u; }
+			}
+			if (level == 0) {
+				const int fx = vx & cell_mask, fy = vy & cell_mask;
+				exact = fx < HMRM_LIN_MARGIN || fy < HMRM_LIN_MARGIN || fx > cell_mask - HMRM_LIN_MARGIN || fy > cell_mask - HMRM_LIN_MARGIN;
+			}
+		}
+
+		unsigned m = 1u;
+		if (!exact && vz - HMRM_LIN_MARGIN > q && q < 65535) {
+			// above every surface value of the neighbourhood (or of the cell): this sample cannot hit
+			if (level > 0) {
+				float est_xy, est_z;
+				int lo_x, hi_x, lo_y, hi_y;
+				for (;;) {
+					const int sh = k + level;
+					const int bx = vx >> sh, by = vy >> sh;
+					lo_x = (max(bx - 1, 0) << sh) + HMRM_LIN_MARGIN;
+					lo_y = (max(by - 1, 0) << sh) + HMRM_LIN_MARGIN;
+					hi_x = (int)min((long long)(bx + 2) << sh, grid_vx) - HMRM_LIN_MARGIN;
+					hi_y = (int)min((long long)(by + 2) << sh, grid_vy) - HMRM_LIN_MARGIN;
+					const float ex_ = __int2float_rz(lx.d >= 0 ? hi_x - vx : vx - lo_x) * inv_adx;
+					const float ey_ = __int2float_rz(ly.d >= 0 ? hi_y - vy : vy - lo_y) * inv_ady;
+					est_xy = fminf(ex_, ey_);
+					est_z = lz.d < 0 ? __int2float_rz(vz - HMRM_LIN_MARGIN - q) * inv_adz : 3.0e38f;
+					// climb while z leaves room for (much) wider blocks and the wider neighbourhood is cleared too
+					if (!(est_z >= 4.0f * est_xy) || level + P.lstride > P.ltop) break;
+					const int q2 = probe(level + P.lstride, vx, vy);
+					if (kStats) fetches += 1u;
+					if (!(vz - HMRM_LIN_MARGIN > q2 && q2 < 65535)) break;
+					level += P.lstride;
+					q = q2;
+				}
+				const float est = fminf(fminf(est_xy, est_z), (float)(HMRM_LIN_PERIOD - j)) * 0.999f;
+				m = (est >= 2.0f) ? (unsigned)__float2int_rz(est) : 1u;
+				// samples n .. n+m-1 are skipped: sample n+m (examined next) must still be inside the cleared region
+				while (m >= 2u) {
+					const long long ux = lin_at(lx, j + m), uy = lin_at(ly, j + m), uz = lin_at(lz, j + m);
+					if (ux >= lo_x && ux < hi_x && uy >= lo_y && uy < hi_y && uz - HMRM_LIN_MARGIN > q) break;
+					if (kStats) tally.dbg[6] += 1u;
+					m -= 1u + (m >> 3);
+				}
+				if (m < 1u) m = 1u;
+				if (kStats) {
+					if (m >= 2u) { tally.dbg[0] += 1u; tally.dbg[1] += m; }
+					else tally.dbg[2] += 1u;
+				}
+				// a z-limited jump ends just above q: the next sample will need a finer level
+				if (est_z < est_xy) level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
+			}
+			else {
+				if (kStats) tally.dbg[4] += 1u;
+				if (vz - q > cell_exit) level = P.lmin;
+			}
+		}
+		else if (!exact && vz + HMRM_LIN_MARGIN < q && q > 0) {    // q == 0 may be a clamped value: proves nothing
+			// level 0, cell known, clearly below the surface: the reference's test `z < surf` holds (main/hmap.cpp:1016)
+			const size_t cell = (size_t)(vx >> k) + (size_t)(vy >> k) * (size_t)P.map_w;
+			if (kStats) tally.dbg[5] += 1u;
+			rgba = hit_colour(P, __ldg(P.color + cell));
+			real_hit = true;
+			first_hit = (n > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)n;
+			n += 1u;
+			finished = true;
+			break;
+		}
+		else {
+			// undecided within the margin: reconstruct the exact sample and let the reference's own expressions decide
+			if (kStats) tally.dbg[7] += 1u;
+			advance_exact(ax, ay, az, anchor, n);
+			const int gx = trunc_cell(fdiv(ax.p, P.gw)), gy = trunc_cell(fdiv(-ay.p, P.gw));
+			if (gx < 0 || gy < 0 || gx >= P.map_w || gy >= P.map_h) {
+				finished = true;
+				break;
+			}
+			const size_t cell = (size_t)gx + (size_t)gy * (size_t)P.map_w;
+			if (kStats) fetches += 1u;
+			if (az.p < __ldg(P.surf + cell)) {
+				rgba = hit_colour(P, __ldg(P.color + cell));
+				real_hit = true;
+				first_hit = (n > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)n;
+				n += 1u;
+				finished = true;
+				break;
+			}
+			level = 0;
+		}
+		n += m;
+		if (n >= 0x7FF00000u) {          // ~2^31 samples: give up like a hang would, but flagged
+			tally.cut_off = 1u;
+			finished = true;
+			break;
+		}
+	}
+	}   // if (model)
+
+	if (!finished) {
+		// The plain per-step loop (k2_render_brute.cuh) from the exact anchor on, with a cap instead of a hang: rays
+		// that do not fit the integer model, and rays that left its representable range.
+		advance_exact(ax, ay, az, anchor, n);
+		unsigned long long kk = n;
+		for (;;) {
+			const int gx = trunc_cell(fdiv(ax.p, P.gw)), gy = trunc_cell(fdiv(-ay.p, P.gw));
+			if (gx < 0 || gy < 0 || gx >= P.map_w || gy >= P.map_h) break;
+			const size_t cell = (size_t)gx + (size_t)gy * (size_t)P.map_w;
+			kk += 1ULL;
+			if (kStats) fetches += 1u;
+			if (az.p < __ldg(P.surf + cell)) {
+				rgba = hit_colour(P, __ldg(P.color + cell));
+				real_hit = true;
+				first_hit = (kk - 1ULL > 0x7FFFFFFFULL) ? 0x7FFFFFFF : (int)(kk - 1ULL);
+				break;
+			}
+			const double nx = fadd(ax.p, ax.s), ny = fadd(ay.p, ay.s), nz = fadd(az.p, az.s);
+			if ((nx == ax.p && ny == ay.p && !(nz < az.p)) || kk >= (1ULL << 27)) {
+				tally.cut_off = 1u;
+				break;
+			}
+			ax.p = nx; ay.p = ny; az.p = nz;
+		}
+		tally.steps = kk;
+		tally.fetches = fetches;
+		return;
+	}
+	tally.steps = n;
+	tally.fetches = fetches;
+}
+
+template <bool kStats, bool kFast>
+__global__ void __launch_bounds__(256, 4) k2_render_lin(const __grid_constant__ RenderParams P) {
+	const int lane = threadIdx.x & 31;
+	const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
+
+	for (;;) {
+		const unsigned tile = next_tile(P.tile_counter);
+		if (tile >= n_tiles) break;
+		const int ty_seq = (int)(tile / (unsigned)P.tiles_x);
+		const int tx = (int)(tile - (unsigned)ty_seq * (unsigned)P.tiles_x);
+		// longest-processing-time-first: a few grazing tiles take ~50x the mean, so they must start early
+		const int ty = P.row_order ? __ldg(P.row_order + ty_seq) : ty_seq;
+		const int px = tx * 8 + (lane & 7);
+		const int py = P.row_begin + (P.tile_y_first + ty * P.tile_y_step) * 4 + (lane >> 3);
+		const bool active = pixel_selected(P, px, py);
+
+		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u, {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};
+		if (active) {
+			uint32_t rgba = 0u;
+			bool real_hit = false;
+			int first_hit = -1;
+			if (!(kFast && fast_miss(P, px, py, rgba))) {
+				const Ray ray = generate_ray(P, px, py);
+				double ex, ey, ez;
+				if (box_entry(P, ray, ex, ey, ez)) {
+					tally.box_hit = 1u;
+					first_hit = -2;
+					march_lin<kStats>(P, ray, ex, ey, ez, rgba, real_hit, first_hit, tally);
+				}
+				if (!real_hit) rgba = miss_colour(P, ray.dz);
+				else tally.surf_hit = 1u;
+			}
+			P.fb[(size_t)py * (size_t)P.W + (size_t)px] = rgba;
+			if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
+		}
+		commit_tally<kStats>(P, active, tally);
+	}
+}
+
+} // namespace hmrm
+
+#endif

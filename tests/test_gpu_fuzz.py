@@ -99,14 +99,15 @@ def test_random_cases_match_oracle(hmrm, renderer, oracle, seed):
         fb = renderer.frame(traversal=1, flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX, **fk)
         a = renderer.render(fb).copy()
         sa, ia = renderer.stats(), renderer.step_index(fb)
-        fs = renderer.frame(traversal=2, flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX, **fk)
-        b = renderer.render(fs).copy()
-        sb, ib = renderer.stats(), renderer.step_index(fs)
         tag = f"seed {seed} case {i}: {fk} map {case['hm'].shape} lum {case['lum']} h [{case['min_height']},{case['max_height']}]"
-        assert sa.status == sb.status, tag
-        assert np.array_equal(a, b), tag
-        assert np.array_equal(ia, ib), tag
-        assert (sa.steps, sa.box_hits, sa.surf_hits, sa.max_steps) == (sb.steps, sb.box_hits, sb.surf_hits, sb.max_steps), tag
+        for trav in (2, 3):
+            fs = renderer.frame(traversal=trav, flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX, **fk)
+            b = renderer.render(fs).copy()
+            sb, ib = renderer.stats(), renderer.step_index(fs)
+            assert sa.status == sb.status, (trav, tag)
+            assert np.array_equal(a, b), (trav, tag)
+            assert np.array_equal(ia, ib), (trav, tag)
+            assert (sa.steps, sa.box_hits, sa.surf_hits, sa.max_steps) == (sb.steps, sb.box_hits, sb.surf_hits, sb.max_steps), (trav, tag)
         if sa.status == 0 and sa.max_steps < 3_000_000:
             want, osteps, ost = oracle.render(of, heights, case["cm"])
             assert np.array_equal(a, want), tag
@@ -130,7 +131,7 @@ def check_against_oracle(hmrm, renderer, oracle, hm, cm, lum, mn, mx, fk, tag):
     heights = oracle.update_heightmap(hm, lum, mn, mx)
     want, osteps, ost = oracle.render(of, heights, cm)
     out = []
-    for trav in (1, 2):
+    for trav in (1, 2, 3):
         f = renderer.frame(traversal=trav, flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX, **fk)
         got = renderer.render(f).copy()
         st, si = renderer.stats(), renderer.step_index(f)

@@ -12,7 +12,7 @@ import scenes as S
 
 pytestmark = pytest.mark.gpu
 
-TRAVERSALS = [1, 2]   # HMRM_TRAVERSAL_BRUTE, HMRM_TRAVERSAL_SKIP
+TRAVERSALS = [1, 2, 3]   # HMRM_TRAVERSAL_BRUTE, _SKIP (integer linear model), _SKIP_FP64
 
 
 @pytest.mark.parametrize("traversal", TRAVERSALS)

@@ -25,7 +25,7 @@ wl = bench.WORKLOADS[args.workload]
 r = hmrm.Renderer(0)
 r.min_height, r.max_height = bench.MIN_HEIGHT, bench.MAX_HEIGHT
 r.synth_maps(wl["log2n"], bench.SEED)
-trav = {"auto": 0, "brute": 1, "skip": 2}[args.traversal]
+trav = {"auto": 0, "brute": 1, "skip": 2, "skip_fp64": 3}[args.traversal]
 for i in range(args.frames):
     c = bench.camera(wl, args.first + i)
     if args.vang is not None:
