@@ -13,14 +13,16 @@
 //       |X(P_j) - X(P_0 + j s)| <= j * 2^-53 * max|X| <= j * 2^-22   (accumulated FP64 rounding of the adds)
 //     and with j < 2^16 between exact re-anchors:   |V_j - X(P_j)| < 1.6 units  (and the reference's rounded
 //     quotient fl(x/gw) differs from x/gw by < 2^-22 units).  Everything the march decides is therefore decided
-//     from V_j with a margin of HMRM_LIN_MARGIN = 4 units:
+//     from V_j with a margin of HMRM_LIN_MARGIN = 4 units in x and y:
 //       * cell index   = V >> k            when V is >= 4 units away from a cell edge,
 //       * inside grid / outside grid       when V is >= 4 units away from the grid edge (the low edge is at -1 cell:
-//                                          (int) truncates toward zero, so (-1, 0) still is cell 0),
-//       * above the (dilated) block max q  when Z_j - 4 > q  (q < 65535: clamped values never prove anything),
-//       * hit                              when Z_j + 4 < q  (q > 0; same monotone Zq16 argument as k2_render_skip.cuh),
+//                                          (int) truncates toward zero, so (-1, 0) still is cell 0).
+//     The height axis is modelled in 1/16 Zq units (same bound, < 1.6/16 Zq), and Zq16(z) = round(Zr(z)) flips at
+//     q +- 1/2, so with HMRM_LIN_ZMARGIN = 8 + 2 sixteenths:
+//       * above the (dilated) block max q  when Z_j > 16 q + 10  (q < 65535: clamped values never prove anything),
+//       * hit                              when Z_j < 16 q - 10  (q > 0; same monotone Zq16 argument as k2_render_skip.cuh),
 //       * a jump of m samples              when samples n and n+m are both >= 4 units inside the cleared
-//                                          neighbourhood and the grid, and both have Z - 4 > q: V is monotone in j.
+//                                          neighbourhood and the grid, and both are above q: V is monotone in j.
 //     Any sample that is NOT decided with that margin is handed to resolve_exact(): the exact FP64 position P_n is
 //     reconstructed from the last exact anchor with the binade-aware closed form (fact 1) and the reference's own
 //     expressions (divide, truncate, compare with the FP64 surface) decide it.  On the bench frame that happens
@@ -37,7 +39,8 @@ namespace hmrm {
 
 #define HMRM_LIN_FRAC 16
 #define HMRM_LIN_PERIOD 65536u      // samples between exact re-anchors (keeps the error bound of fact 4)
-#define HMRM_LIN_MARGIN 4
+#define HMRM_LIN_MARGIN 4         // x, y: fixed-point units
+#define HMRM_LIN_ZMARGIN 10       // z: 1/16 Zq units = 8 (Zq16 rounds at q +- 1/2) + 2 (model error < 1.6)
 
 // Move the exact anchor (sample index a, position in ax/ay/az.p) forward to sample n.  Exact: closed form inside
 // binades (end point checked), plain adds across them.
@@ -113,15 +116,21 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 	unsigned fetches = 0u;
 
 	// ---- integer model of this ray ----
+	// x, y in fixed-point units (2^-k cells); z in 1/16 Zq units: the extra 4 bits shrink the band in which the model
+	// cannot tell `above` from `hit` to ~1.3 Zq units.  Zr(z) = z * zq_scale + c with an integer c, so 16 Zr has the
+	// same magic-number form.
+	const double zc = P.zq_offset - HMRM_MAGIC;
+	const double zs16 = P.zq_scale * 16.0, zo16 = __fma_rn(16.0, zc, HMRM_MAGIC);
 	LinAxis lx, ly, lz;
-	bool model = lin_slope(ax.s * P.fx_scale, lx.d) && lin_slope(-ay.s * P.fx_scale, ly.d) && lin_slope(az.s * P.zq_scale, lz.d);
+	bool model = lin_slope(ax.s * P.fx_scale, lx.d) && lin_slope(-ay.s * P.fx_scale, ly.d) && lin_slope(az.s * zs16, lz.d);
+	model = model && fabs(zc) < 1.0e12;
 	// no lateral motion and not coming down: such a ray can only end by the reference's hang; the per-step loop cuts it
 	model = model && (lx.d != 0 || ly.d != 0 || lz.d < 0);
 	auto rebase = [&]() -> bool {                     // V_0 of the model := the exact anchor
 		int vx, vy, vz;
 		const bool okx = magic_decode(__fma_rn(ax.p, P.fx_scale, HMRM_MAGIC), vx);
 		const bool oky = magic_decode(__fma_rn(ay.p, -P.fx_scale, HMRM_MAGIC), vy);
-		const bool okz = magic_decode(__fma_rn(az.p, P.zq_scale, P.zq_offset), vz);
+		const bool okz = magic_decode(__fma_rn(az.p, zs16, zo16), vz);
 		lx.v0 = vx; ly.v0 = vy; lz.v0 = vz;
 		return okx && oky && okz;
 	};
@@ -134,17 +143,22 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 	const float inv_ady = fast_rcp(fabsf((float)ly.d) * (1.0f / 65536.0f));
 	const float adz = fabsf((float)lz.d) * (1.0f / 65536.0f);
 	const float inv_adz = fast_rcp(adz);
-	const int cell_exit = (int)fminf(P.cell_exit_scale * adz + 32.0f, 1.0e9f);
+	const int cell_exit = (int)fminf(P.cell_exit_scale * adz + 512.0f, 1.0e9f);
 	const long long grid_vx = (long long)P.map_w << k, grid_vy = (long long)P.map_h << k;   // <= 2^30
+	const unsigned long long span_x = (unsigned long long)(grid_vx - 2 * HMRM_LIN_MARGIN);
+	const unsigned long long span_y = (unsigned long long)(grid_vy - 2 * HMRM_LIN_MARGIN);
 	const int cell_mask = (1 << k) - 1;
 	int level = P.lstart;
 
-	auto probe = [&](int lvl, int vx, int vy) -> int {
+	auto probe = [&](int lvl, int vx, int vy) -> int {   // dilated block maximum, in the z units of the model
 		const uint2 d = P.lv_desc[lvl];
 		const unsigned idx = d.x + (unsigned)(vy >> (k + lvl)) * d.y + (unsigned)(vx >> (k + lvl));
 		return (int)__ldg(P.lv + idx);
 	};
+	// `above q` / `below q` with the model's error (< 1.6/16 Zq) and Zq16's rounding (ties at q +- 1/2) covered
+	auto above = [&](int vz, int q) -> bool { return vz > (q << 4) + HMRM_LIN_ZMARGIN && q < 65535; };
 
+	long long wx = lin_at(lx, 0u), wy = lin_at(ly, 0u), wz = lin_at(lz, 0u);   // model position of sample n
 	for (;;) {
 		// keep the error bound: re-anchor the model on an exact position every HMRM_LIN_PERIOD samples
 		if (n - base >= HMRM_LIN_PERIOD) {
@@ -154,30 +168,30 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 				model = false;
 				break;
 			}
+			wx = lin_at(lx, 0u); wy = lin_at(ly, 0u); wz = lin_at(lz, 0u);
 		}
 		const unsigned j = n - base;
-		const long long wx = lin_at(lx, j), wy = lin_at(ly, j);
-		// Certainly outside the grid (main/hmap.cpp:1006-1011)?  The reference truncates toward zero (:1001-1004), so
-		// coordinates in (-1, 0) cells still map to cell 0: the low edge of the grid is at -1 cell, not at 0.
-		const long long low_edge = -(1LL << k) - HMRM_LIN_MARGIN;
-		if (wx < low_edge || wy < low_edge || wx >= grid_vx + HMRM_LIN_MARGIN || wy >= grid_vy + HMRM_LIN_MARGIN) {
-			finished = true;
-			break;
+		// does this sample need the exact treatment?  (within the margin of the grid edge; at level 0 also of a cell edge)
+		bool exact = false;
+		if (!((unsigned long long)(wx - HMRM_LIN_MARGIN) < span_x && (unsigned long long)(wy - HMRM_LIN_MARGIN) < span_y)) {
+			// Certainly outside the grid (main/hmap.cpp:1006-1011)?  The reference truncates toward zero (:1001-1004), so
+			// coordinates in (-1, 0) cells still map to cell 0: the low edge of the grid is at -1 cell, not at 0.
+			const long long low_edge = -(1LL << k) - HMRM_LIN_MARGIN;
+			if (wx < low_edge || wy < low_edge || wx >= grid_vx + HMRM_LIN_MARGIN || wy >= grid_vy + HMRM_LIN_MARGIN) {
+				finished = true;
+				break;
+			}
+			exact = true;         // (the whole (-1, 0] strip of the truncation quirk goes the exact way too)
 		}
 		const int vx = (int)wx, vy = (int)wy;
-		long long wz = lin_at(lz, j);
-		wz = wz < -1073741824LL ? -1073741824LL : (wz > 1073741824LL ? 1073741824LL : wz);
-		const int vz = (int)wz;
+		const int vz = (int)(wz < -1073741824LL ? -1073741824LL : (wz > 1073741824LL ? 1073741824LL : wz));
 
-		// does this sample need the exact treatment?  (within the margin of the grid edge; at level 0 also of a cell edge)
-		// (everything below +4 units, i.e. the whole (-1, 0] strip of the truncation quirk, goes the exact way too)
-		bool exact = vx < HMRM_LIN_MARGIN || vy < HMRM_LIN_MARGIN || wx >= grid_vx - HMRM_LIN_MARGIN || wy >= grid_vy - HMRM_LIN_MARGIN;
 		int q = 0;
 		if (!exact) {
 			// ---- A: find a level whose neighbourhood this sample clears (descend), or reach the cell itself ----
 			q = probe(level, vx, vy);
 			if (kStats) fetches += 1u;
-			while (!(vz - HMRM_LIN_MARGIN > q && q < 65535) && level > 0) {
+			while (!above(vz, q) && level > 0) {
 				level = (level - P.lstride >= P.lmin) ? level - P.lstride : 0;
 				q = probe(level, vx, vy);
 				if (kStats) { fetches += 1u; tally.dbg[3] += 1u; }
@@ -189,7 +203,8 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		}
 
 		unsigned m = 1u;
-		if (!exact && vz - HMRM_LIN_MARGIN > q && q < 65535) {
+		bool carried = false;      // wx/wy/wz already hold sample n+m
+		if (!exact && above(vz, q)) {
 			// above every surface value of the neighbourhood (or of the cell): this sample cannot hit
 			if (level > 0) {
 				float est_xy, est_z;
@@ -204,21 +219,26 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 					const float ex_ = __int2float_rz(lx.d >= 0 ? hi_x - vx : vx - lo_x) * inv_adx;
 					const float ey_ = __int2float_rz(ly.d >= 0 ? hi_y - vy : vy - lo_y) * inv_ady;
 					est_xy = fminf(ex_, ey_);
-					est_z = lz.d < 0 ? __int2float_rz(vz - HMRM_LIN_MARGIN - q) * inv_adz : 3.0e38f;
+					est_z = lz.d < 0 ? __int2float_rz(vz - (q << 4) - HMRM_LIN_ZMARGIN) * inv_adz : 3.0e38f;
 					// climb while z leaves room for (much) wider blocks and the wider neighbourhood is cleared too
 					if (!(est_z >= 4.0f * est_xy) || level + P.lstride > P.ltop) break;
 					const int q2 = probe(level + P.lstride, vx, vy);
 					if (kStats) fetches += 1u;
-					if (!(vz - HMRM_LIN_MARGIN > q2 && q2 < 65535)) break;
+					if (!above(vz, q2)) break;
 					level += P.lstride;
 					q = q2;
 				}
 				const float est = fminf(fminf(est_xy, est_z), (float)(HMRM_LIN_PERIOD - j)) * 0.999f;
 				m = (est >= 2.0f) ? (unsigned)__float2int_rz(est) : 1u;
 				// samples n .. n+m-1 are skipped: sample n+m (examined next) must still be inside the cleared region
+				const long long qz = (long long)((q << 4) + HMRM_LIN_ZMARGIN);
 				while (m >= 2u) {
 					const long long ux = lin_at(lx, j + m), uy = lin_at(ly, j + m), uz = lin_at(lz, j + m);
-					if (ux >= lo_x && ux < hi_x && uy >= lo_y && uy < hi_y && uz - HMRM_LIN_MARGIN > q) break;
+					if (ux >= lo_x && ux < hi_x && uy >= lo_y && uy < hi_y && uz > qz) {
+						wx = ux; wy = uy; wz = uz;
+						carried = true;
+						break;
+					}
 					if (kStats) tally.dbg[6] += 1u;
 					m -= 1u + (m >> 3);
 				}
@@ -232,10 +252,10 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			}
 			else {
 				if (kStats) tally.dbg[4] += 1u;
-				if (vz - q > cell_exit) level = P.lmin;
+				if (vz - (q << 4) > cell_exit) level = P.lmin;
 			}
 		}
-		else if (!exact && vz + HMRM_LIN_MARGIN < q && q > 0) {    // q == 0 may be a clamped value: proves nothing
+		else if (!exact && vz < (q << 4) - HMRM_LIN_ZMARGIN && q > 0) {    // q == 0 may be a clamped value: proves nothing
 			// level 0, cell known, clearly below the surface: the reference's test `z < surf` holds (main/hmap.cpp:1016)
 			const size_t cell = (size_t)(vx >> k) + (size_t)(vy >> k) * (size_t)P.map_w;
 			if (kStats) tally.dbg[5] += 1u;
@@ -268,6 +288,10 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			level = 0;
 		}
 		n += m;
+		if (!carried) {
+			const unsigned jn = n - base;
+			wx = lin_at(lx, jn); wy = lin_at(ly, jn); wz = lin_at(lz, jn);
+		}
 		if (n >= 0x7FF00000u) {          // ~2^31 samples: give up like a hang would, but flagged
 			tally.cut_off = 1u;
 			finished = true;
