@@ -33,6 +33,7 @@ namespace {
 std::string g_create_error;
 
 const int kLaunchSlots = 4;
+const int kFrameRing = 3;      // device frame buffers (and compute streams) whole frames rotate through
 
 // Everything one launch writes before / while its kernel runs.  A slot is reused only after the kernel that used
 // it last has finished (ev_end), so up to kLaunchSlots frames of one context may be in flight on any streams.
@@ -56,7 +57,8 @@ struct hmrm_ctx {
 	int device;
 	int num_sms;
 	cudaStream_t stream;          // compute stream of frame-buffer slot 0 (and of everything that is not a frame)
-	cudaStream_t stream_alt;      // compute stream of frame-buffer slot 1: frame n+1 starts while frame n's tail drains
+	cudaStream_t ring_stream[kFrameRing];   // compute stream of each frame buffer ([0] == stream): frame n+1 starts
+	                                        // while frame n's tail drains
 	std::string err;
 
 	// maps
@@ -83,12 +85,13 @@ struct hmrm_ctx {
 	double *d_wtab, *d_htab;
 
 	// outputs
-	uint32_t *d_fb;              // the persistent framebuffer (the reference's framebuf, main/hmap.cpp:612)
-	uint32_t *d_fb_alt;          // second buffer so that frame n+1 can render while frame n is copied out
+	uint32_t *d_fb[kFrameRing];  // [0]: the persistent framebuffer (the reference's framebuf, main/hmap.cpp:612);
+	                             // whole frames rotate through all of them so that frames n+1, n+2 render while frame
+	                             // n is copied out
 	int fb_w, fb_h;
 	cudaStream_t copy_stream;
-	cudaEvent_t ev_rendered[2], ev_copied[2];
-	bool copy_pending[2];
+	cudaEvent_t ev_rendered[kFrameRing], ev_copied[kFrameRing];
+	bool copy_pending[kFrameRing];
 	int slot;                    // buffer of the most recent hmrm_render_async
 	int32_t *d_step_index;
 	size_t step_index_cap;
@@ -139,8 +142,7 @@ __global__ void __launch_bounds__(256) k_synth_maps(uint32_t log2n, uint32_t see
 }
 
 int drain(hmrm_ctx *c) {
-	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
-	HMRM_CUDA(c, cudaStreamSynchronize(c->stream_alt));
+	for (int i = 0; i < kFrameRing; ++i) HMRM_CUDA(c, cudaStreamSynchronize(c->ring_stream[i]));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	// kernels launched on the caller's streams (hmrm_render_device) are tracked by their slot's end event
 	for (int i = 0; i < kLaunchSlots; ++i) {
@@ -216,17 +218,19 @@ int ensure_tables(hmrm_ctx *c, int W, int H) {
 }
 
 int ensure_framebuffer(hmrm_ctx *c, int W, int H) {
-	if (c->d_fb && c->fb_w == W && c->fb_h == H) return HMRM_OK;
+	if (c->d_fb[0] && c->fb_w == W && c->fb_h == H) return HMRM_OK;
 	if (int rc = drain(c)) return rc;
-	c->copy_pending[0] = c->copy_pending[1] = false;
-	cudaFree(c->d_fb);
-	cudaFree(c->d_fb_alt);
-	c->d_fb = c->d_fb_alt = NULL;
-	HMRM_CUDA(c, cudaMalloc(&c->d_fb, (size_t)W * (size_t)H * 4));
-	HMRM_CUDA(c, cudaMalloc(&c->d_fb_alt, (size_t)W * (size_t)H * 4));
-	// the reference's framebuf starts uninitialised (main/hmap.cpp:612); start from zeros instead
-	HMRM_CUDA(c, cudaMemset(c->d_fb, 0, (size_t)W * (size_t)H * 4));
-	HMRM_CUDA(c, cudaMemset(c->d_fb_alt, 0, (size_t)W * (size_t)H * 4));
+	for (int i = 0; i < kFrameRing; ++i) {
+		c->copy_pending[i] = false;
+		cudaFree(c->d_fb[i]);
+		c->d_fb[i] = NULL;
+	}
+	c->fb_w = c->fb_h = 0;
+	for (int i = 0; i < kFrameRing; ++i) {
+		HMRM_CUDA(c, cudaMalloc(&c->d_fb[i], (size_t)W * (size_t)H * 4));
+		// the reference's framebuf starts uninitialised (main/hmap.cpp:612); start from zeros instead
+		HMRM_CUDA(c, cudaMemset(c->d_fb[i], 0, (size_t)W * (size_t)H * 4));
+	}
 	c->slot = 0;
 	c->fb_w = W;
 	c->fb_h = H;
@@ -560,7 +564,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->device = device;
 	c->num_sms = prop.multiProcessorCount;
 	c->stream = NULL;
-	c->stream_alt = NULL;
+	for (int i = 0; i < kFrameRing; ++i) c->ring_stream[i] = NULL;
 	c->last_stream = NULL;
 	c->map_w = c->map_h = 0;
 	c->d_rgb = NULL;
@@ -583,11 +587,13 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->tab_w = c->tab_h = 0;
 	c->d_wtab = c->d_htab = NULL;
 	std::memset(c->slots, 0, sizeof c->slots);
-	c->d_fb = c->d_fb_alt = NULL;
+	for (int i = 0; i < kFrameRing; ++i) {
+		c->d_fb[i] = NULL;
+		c->copy_pending[i] = false;
+		c->ev_rendered[i] = c->ev_copied[i] = NULL;
+	}
 	c->fb_w = c->fb_h = 0;
 	c->copy_stream = NULL;
-	c->copy_pending[0] = c->copy_pending[1] = false;
-	c->ev_rendered[0] = c->ev_rendered[1] = c->ev_copied[0] = c->ev_copied[1] = NULL;
 	c->slot = 0;
 	c->d_step_index = NULL;
 	c->step_index_cap = 0;
@@ -599,11 +605,12 @@ int hmrm_create(int device, hmrm_ctx **out) {
 
 	cudaError_t err = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
 	if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
-	for (int i = 0; i < 2 && err == cudaSuccess; ++i) {
+	c->ring_stream[0] = c->stream;
+	for (int i = 0; i < kFrameRing && err == cudaSuccess; ++i) {
 		err = cudaEventCreateWithFlags(&c->ev_rendered[i], cudaEventDisableTiming);
 		if (err == cudaSuccess) err = cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming);
+		if (err == cudaSuccess && i > 0) err = cudaStreamCreateWithFlags(&c->ring_stream[i], cudaStreamNonBlocking);
 	}
-	if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->stream_alt, cudaStreamNonBlocking);
 	for (int i = 0; i < kLaunchSlots && err == cudaSuccess; ++i) {
 		err = cudaEventCreate(&c->slots[i].ev_begin);
 		if (err == cudaSuccess) err = cudaEventCreate(&c->slots[i].ev_end);
@@ -623,17 +630,17 @@ int hmrm_create(int device, hmrm_ctx **out) {
 void hmrm_destroy(hmrm_ctx *c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
-	if (c->stream) cudaStreamSynchronize(c->stream);
-	if (c->stream_alt) cudaStreamSynchronize(c->stream_alt);
+	for (int i = 0; i < kFrameRing; ++i) {
+		if (c->ring_stream[i]) cudaStreamSynchronize(c->ring_stream[i]);
+	}
 	free_maps(c);
 	cudaFree(c->d_max_bits);
 	cudaFree(c->d_wtab);
 	cudaFree(c->d_htab);
 
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
-	cudaFree(c->d_fb);
-	cudaFree(c->d_fb_alt);
-	for (int i = 0; i < 2; ++i) {
+	for (int i = 0; i < kFrameRing; ++i) {
+		cudaFree(c->d_fb[i]);
 		if (c->ev_rendered[i]) cudaEventDestroy(c->ev_rendered[i]);
 		if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
 	}
@@ -649,8 +656,9 @@ void hmrm_destroy(hmrm_ctx *c) {
 		if (sl.ev_begin) cudaEventDestroy(sl.ev_begin);
 		if (sl.ev_end) cudaEventDestroy(sl.ev_end);
 	}
-	if (c->stream) cudaStreamDestroy(c->stream);
-	if (c->stream_alt) cudaStreamDestroy(c->stream_alt);
+	for (int i = 0; i < kFrameRing; ++i) {
+		if (c->ring_stream[i]) cudaStreamDestroy(c->ring_stream[i]);
+	}
 	delete c;
 }
 
@@ -841,20 +849,21 @@ int hmrm_render_async(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
 	HMRM_CUDA(c, cudaSetDevice(c->device));
 	int rc = ensure_framebuffer(c, f->screen_width, f->screen_height);
 	if (rc) return rc;
-	// Whole frames (cycle_period 1) alternate between two device buffers so that the copy-out of frame n overlaps
-	// the kernel of frame n+1; the progressive interleave (cycle_period > 1) accumulates in the one persistent buffer.
-	// Each buffer has its own compute stream, so the kernel of frame n+1 starts filling SMs as the CTAs of frame n
-	// run out of tiles (a handful of grazing tiles take ~50x the mean: the tail of a frame leaves most SMs idle).
+	// Whole frames (cycle_period 1) rotate through kFrameRing device buffers so that the copy-out of frame n overlaps
+	// the kernels of frames n+1 and n+2; the progressive interleave (cycle_period > 1) accumulates in the one
+	// persistent buffer.  Each buffer has its own compute stream, so the kernel of the next frame starts filling SMs as
+	// the CTAs of this one run out of tiles (a handful of grazing tiles take ~50x the mean: the tail of a frame
+	// leaves most SMs idle).
 	const bool whole = f->cycle_period == 1 && (f->flags & HMRM_FLAG_STEP_INDEX) == 0;
-	const int slot = whole ? (c->slot ^ 1) : 0;
-	uint32_t *fb = slot ? c->d_fb_alt : c->d_fb;
-	cudaStream_t cs = slot ? c->stream_alt : c->stream;
+	const int slot = whole ? (c->slot + 1) % kFrameRing : 0;
+	uint32_t *fb = c->d_fb[slot];
+	cudaStream_t cs = c->ring_stream[slot];
 	if (!whole) {
 		// progressive frames and step-index captures are ordered after everything else
-		HMRM_CUDA(c, cudaStreamSynchronize(c->stream_alt));
-		if (f->cycle_period != 1 && c->slot == 1) {
-			// the newest picture lives in the alternate buffer: a progressive frame must land on top of it
-			HMRM_CUDA(c, cudaMemcpyAsync(c->d_fb, c->d_fb_alt, (size_t)c->fb_w * (size_t)c->fb_h * 4,
+		for (int i = 1; i < kFrameRing; ++i) HMRM_CUDA(c, cudaStreamSynchronize(c->ring_stream[i]));
+		if (f->cycle_period != 1 && c->slot != 0) {
+			// the newest picture lives in another buffer of the ring: a progressive frame must land on top of it
+			HMRM_CUDA(c, cudaMemcpyAsync(c->d_fb[0], c->d_fb[c->slot], (size_t)c->fb_w * (size_t)c->fb_h * 4,
 			                             cudaMemcpyDeviceToDevice, cs));
 		}
 	}
@@ -878,18 +887,19 @@ int hmrm_wait_pending(hmrm_ctx *c, int max_pending) {
 	if (!c) return HMRM_ERR_INVALID;
 	HMRM_CUDA(c, cudaSetDevice(c->device));
 	if (max_pending >= 1) {
-		// let the most recent frame stay in flight; the one before it must be on the host
-		const int older = c->slot ^ 1;
-		if (c->copy_pending[older]) {
-			HMRM_CUDA(c, cudaEventSynchronize(c->ev_copied[older]));
-			c->copy_pending[older] = false;
+		// let the max_pending most recent frames stay in flight; the ones before them must be on the host
+		for (int age = kFrameRing - 1; age >= max_pending; --age) {
+			const int older = (c->slot + kFrameRing - age) % kFrameRing;
+			if (c->copy_pending[older]) {
+				HMRM_CUDA(c, cudaEventSynchronize(c->ev_copied[older]));
+				c->copy_pending[older] = false;
+			}
 		}
 		return HMRM_OK;
 	}
-	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
-	HMRM_CUDA(c, cudaStreamSynchronize(c->stream_alt));
+	for (int i = 0; i < kFrameRing; ++i) HMRM_CUDA(c, cudaStreamSynchronize(c->ring_stream[i]));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
-	c->copy_pending[0] = c->copy_pending[1] = false;
+	for (int i = 0; i < kFrameRing; ++i) c->copy_pending[i] = false;
 	return HMRM_OK;
 }
 

@@ -137,24 +137,28 @@ def test_render_device_and_async_paths_agree(hmrm, renderer, oracle):
     assert np.array_equal(pinned, want)
 
 
-def test_streaming_async_frames_equal_synchronous_frames(hmrm, renderer, oracle):
-    """hmrm_render_async + hmrm_wait_pending(1): two frames in flight (copy-out overlaps the next kernel)."""
+@pytest.mark.parametrize("depth", [1, 2])
+def test_streaming_async_frames_equal_synchronous_frames(hmrm, renderer, oracle, depth):
+    """hmrm_render_async + hmrm_wait_pending(depth): depth+1 frames in flight (copy-out overlaps the next kernels)."""
     from heightmap_ray_marcher_b200 import binding
 
     scene = S.SCENE_BY_NAME["persp_graze"]
     maps = H.load_scene_maps(scene, oracle)
     H.configure(renderer, scene, maps)
-    cams = [(-0.5 + 0.1 * i, 0.5 - 0.05 * i, 2.0 + 0.1 * i) for i in range(6)]
+    cams = [(-0.5 + 0.1 * i, 0.5 - 0.05 * i, 2.0 + 0.1 * i) for i in range(8)]
     want = [renderer.render(H.product_frame(hmrm, renderer, scene, cam_pos=c)).copy() for c in cams]
-    bufs = [binding.pinned_empty(want[0].shape), binding.pinned_empty(want[0].shape)]
+    nb = depth + 1
+    bufs = [binding.pinned_empty(want[0].shape) for _ in range(nb)]
     got = []
     for i, c in enumerate(cams):
-        renderer.render_async(H.product_frame(hmrm, renderer, scene, cam_pos=c), bufs[i & 1])
-        renderer.wait_pending(1)
-        if i >= 1:
-            got.append(bufs[(i - 1) & 1].copy())      # frame i-1 is complete, frame i may still be in flight
+        renderer.render_async(H.product_frame(hmrm, renderer, scene, cam_pos=c), bufs[i % nb])
+        renderer.wait_pending(depth)
+        if i >= depth:
+            got.append(bufs[(i - depth) % nb].copy())  # frame i-depth is complete, the newer ones may be in flight
     renderer.wait()
-    got.append(bufs[(len(cams) - 1) & 1].copy())
+    for i in range(len(cams) - depth, len(cams)):
+        got.append(bufs[i % nb].copy())
+    assert len(got) == len(want)
     for i, (g, w) in enumerate(zip(got, want)):
         assert np.array_equal(g, w), f"frame {i}"
     # a progressive (cycle_period > 1) frame after whole frames lands on top of the newest picture
