@@ -457,21 +457,22 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		P.zq_scale = c->zq_scale;
 		P.zq_offset = c->zq_offset;
 		P.ltop = c->mip_levels - 1;
-		// lowest useful block: about two steps wide
+		// lowest useful block: about one step wide (measured: profiles/r01_knob_sweep.txt)
 		const double step_cells = f->step_dist / f->grid_width;
 		int lmin = 1;
-		while (lmin < P.ltop && (double)(1 << lmin) < 2.0 * step_cells) lmin += 1;
+		while (lmin < P.ltop && (double)(1 << lmin) < step_cells) lmin += 1;
 		// tuning knobs for experiments (never affect results, only how many fetches are issued)
 		const char *e_bias = std::getenv("HMRM_LMIN_BIAS"), *e_stride = std::getenv("HMRM_LSTRIDE");
-		const char *e_exit = std::getenv("HMRM_CELL_EXIT");
+		const char *e_exit = std::getenv("HMRM_CELL_EXIT"), *e_start = std::getenv("HMRM_LSTART");
 		if (e_bias) lmin += std::atoi(e_bias);
 		if (lmin < 1) lmin = 1;
 		if (lmin > P.ltop) lmin = P.ltop;
 		P.lmin = lmin;
-		P.lstride = e_stride ? std::atoi(e_stride) : 2;
+		P.lstride = e_stride ? std::atoi(e_stride) : 1;
 		if (P.lstride < 1) P.lstride = 1;
-		P.cell_exit_scale = e_exit ? (float)std::atof(e_exit) : 4.0f;
-		P.lstart = lmin + 2 * P.lstride <= P.ltop ? lmin + 2 * P.lstride : lmin;
+		P.cell_exit_scale = e_exit ? (float)std::atof(e_exit) : 8.0f;
+		const int lstart = lmin + (e_start ? std::atoi(e_start) : 6) * P.lstride;
+		P.lstart = lstart > P.ltop ? P.ltop : (lstart < lmin ? lmin : lstart);
 		if (P.fx_bits < 1) traversal = HMRM_TRAVERSAL_BRUTE;
 		P.lv = c->d_mip;
 		for (int l = 0; l < 16; ++l) {

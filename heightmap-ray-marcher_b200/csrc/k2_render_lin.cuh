@@ -145,8 +145,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 	const float inv_adz = fast_rcp(adz);
 	const int cell_exit = (int)fminf(P.cell_exit_scale * adz + 512.0f, 1.0e9f);
 	const long long grid_vx = (long long)P.map_w << k, grid_vy = (long long)P.map_h << k;   // <= 2^30
-	const unsigned long long span_x = (unsigned long long)(grid_vx - 2 * HMRM_LIN_MARGIN);
-	const unsigned long long span_y = (unsigned long long)(grid_vy - 2 * HMRM_LIN_MARGIN);
+	const unsigned span_x = (unsigned)(grid_vx - 2 * HMRM_LIN_MARGIN), span_y = (unsigned)(grid_vy - 2 * HMRM_LIN_MARGIN);
 	const int cell_mask = (1 << k) - 1;
 	int level = P.lstart;
 
@@ -173,7 +172,10 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		const unsigned j = n - base;
 		// does this sample need the exact treatment?  (within the margin of the grid edge; at level 0 also of a cell edge)
 		bool exact = false;
-		if (!((unsigned long long)(wx - HMRM_LIN_MARGIN) < span_x && (unsigned long long)(wy - HMRM_LIN_MARGIN) < span_y)) {
+		// (grid extents are <= 2^30 units, so "inside by the margin" is a 32-bit statement once the high words are zero)
+		const bool inside = ((unsigned)((unsigned long long)wx >> 32) | (unsigned)((unsigned long long)wy >> 32)) == 0u &&
+		                    (unsigned)wx - (unsigned)HMRM_LIN_MARGIN < span_x && (unsigned)wy - (unsigned)HMRM_LIN_MARGIN < span_y;
+		if (!inside) {
 			// Certainly outside the grid (main/hmap.cpp:1006-1011)?  The reference truncates toward zero (:1001-1004), so
 			// coordinates in (-1, 0) cells still map to cell 0: the low edge of the grid is at -1 cell, not at 0.
 			const long long low_edge = -(1LL << k) - HMRM_LIN_MARGIN;
