@@ -49,6 +49,7 @@ struct LaunchSlot {
 	int row_cap;
 	double row_key[8];
 	bool row_key_valid;
+	int row_sky_first;           // schedule position of the first tile row that only looks above the horizon
 };
 
 } // namespace
@@ -358,6 +359,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	// first (cost proxy 1/|dir.z| of the centre ray for dir.z < 0).  Depends on the view geometry only, not on the
 	// camera position or heading, so a flythrough computes it once.
 	P.row_order = NULL;
+	P.batch_from_tile = 0xFFFFFFFFu;
 	if (f->projection != HMRM_ORTHOGRAPHIC && P.tiles_y > 1 && !std::getenv("HMRM_NO_ROW_ORDER")) {
 		const double key[8] = {(double)f->projection, (double)W, (double)H, f->vang, f->hfov, (double)row_begin,
 		                       (double)(P.tile_y_first * 65536 + P.tile_y_step), (double)P.tiles_y};
@@ -375,6 +377,16 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 			std::stable_sort(cost.begin(), cost.end());
 			std::vector<int> order((size_t)P.tiles_y);
 			for (int t = 0; t < P.tiles_y; ++t) order[(size_t)t] = cost[(size_t)t].second;
+			// the rows at the end of the schedule whose lowest pixel row still looks up: cheap sky (a hint only)
+			slot.row_sky_first = P.tiles_y;
+			for (int t = P.tiles_y - 1; t >= 0; --t) {
+				int py = row_begin + (P.tile_y_first + order[(size_t)t] * P.tile_y_step) * 4 + 3;
+				if (py > H - 1) py = H - 1;
+				Vec3 pos, dir;
+				plane_ray(pc, 0.5, (double)py / (H - 1), &pos, &dir);
+				if (!(dir.z >= 0.0) || !(cost[(size_t)t].first >= 1.0)) break;
+				slot.row_sky_first = t;
+			}
 			if (P.tiles_y > slot.row_cap) {
 				cudaFree(slot.d_row_order);
 				slot.d_row_order = NULL;
@@ -390,6 +402,12 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 			slot.row_key_valid = true;
 		}
 		P.row_order = slot.d_row_order;
+		// (only when the camera is above the terrain: from below, rows that look up are the expensive ones)
+		if (P.cam[2] > std::fmax(P.c0[2], P.c1[2]) && !std::getenv("HMRM_NO_BATCH"))
+			P.batch_from_tile = (unsigned)slot.row_sky_first * (unsigned)P.tiles_x;
+		if (std::getenv("HMRM_DEBUG_SCHED"))
+			std::fprintf(stderr, "sched: tiles_y %d sky_first %d batch_from %u n_tiles %d\n", P.tiles_y, slot.row_sky_first,
+			             P.batch_from_tile, P.tiles_x * P.tiles_y);
 	}
 
 	// FP32 miss prefilter (see ray_setup.cuh:fast_miss): the box inflated by 2^-12 of the scene scale

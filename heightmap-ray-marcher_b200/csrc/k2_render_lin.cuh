@@ -339,9 +339,21 @@ __global__ void __launch_bounds__(256, 4) k2_render_lin(const __grid_constant__ 
 	const int lane = threadIdx.x & 31;
 	const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
 
+	// Tile queue: one atomic per grab.  Marching tiles are grabbed one at a time (their costs are heavy-tailed and a
+	// wide grab that swallows several heavy tiles doubles the frame time), but the tile rows the host has placed at
+	// the end of the schedule because they look above the horizon are grabbed 8 tiles at a time: a sky tile costs
+	// ~25 ns of SM time and a frame's worth of them is otherwise bound by the single-address atomic.
+	unsigned cur = 0u, end = 0u;
 	for (;;) {
-		const unsigned tile = next_tile(P.tile_counter);
-		if (tile >= n_tiles) break;
+		if (cur == end) {
+			const unsigned batch = (end != 0u && end >= P.batch_from_tile) ? 8u : 1u;
+			unsigned t = 0u;
+			if (lane == 0) t = atomicAdd(P.tile_counter, batch);
+			cur = __shfl_sync(0xFFFFFFFFu, t, 0);
+			end = min(cur + batch, n_tiles);
+			if (cur >= n_tiles) break;
+		}
+		const unsigned tile = cur++;
 		const int ty_seq = (int)(tile / (unsigned)P.tiles_x);
 		const int tx = (int)(tile - (unsigned)ty_seq * (unsigned)P.tiles_x);
 		// longest-processing-time-first: a few grazing tiles take ~50x the mean, so they must start early

@@ -29,6 +29,7 @@ struct RenderParams {
 	int tiles_x, tiles_y;          // 8x4-pixel tiles this launch renders
 	int tile_y_first, tile_y_step; // launch tile row t is frame tile row tile_y_first + t * tile_y_step (row interleave)
 	const int *row_order;          // optional permutation of the launch tile rows: expensive (grazing) rows first
+	unsigned batch_from_tile;      // tiles from this queue position on look above the horizon: grabbed 8 at a time
 	// map
 	int map_w, map_h;
 	// image plane (host-built, frame_setup.h)
