@@ -7,6 +7,7 @@ to the GPU box with the repository snapshot.
 """
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -56,7 +57,8 @@ def is_stale() -> bool:
 def build_lib(force: bool = False, verbose: bool = False) -> Path:
     if not force and not is_stale():
         return LIB
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", str(LIB), *[str(s) for s in sources()]]
+    extra = os.environ.get("HMRM_NVCC_EXTRA", "").split()      # experiments only (e.g. -DHMRM_LIN_THREADS=128)
+    cmd = ["nvcc", *NVCC_FLAGS, *extra, "-o", str(LIB), *[str(s) for s in sources()]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
         print(" ".join(cmd))

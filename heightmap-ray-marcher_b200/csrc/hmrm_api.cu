@@ -511,13 +511,17 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	HMRM_CUDA(c, cudaEventRecord(slot.ev_begin, stream));
 	if (traversal == HMRM_TRAVERSAL_SKIP) {
 		const bool stats_kernel = want_stats || want_steps;
+		const int lin_warps = HMRM_LIN_THREADS / 32;
+		int lin_blocks = c->num_sms * HMRM_LIN_CTAS;
+		if (lin_blocks > (n_tiles + lin_warps - 1) / lin_warps) lin_blocks = (n_tiles + lin_warps - 1) / lin_warps;
+		if (lin_blocks < 1) lin_blocks = 1;
 		if (P.fast_setup) {
-			if (stats_kernel) k2_render_lin<true, true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
-			else k2_render_lin<false, true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+			if (stats_kernel) k2_render_lin<true, true><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);
+			else k2_render_lin<false, true><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);
 		}
 		else {
-			if (stats_kernel) k2_render_lin<true, false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
-			else k2_render_lin<false, false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+			if (stats_kernel) k2_render_lin<true, false><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);
+			else k2_render_lin<false, false><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);
 		}
 	}
 	else if (traversal == HMRM_TRAVERSAL_SKIP_FP64) {

@@ -37,6 +37,14 @@
 
 namespace hmrm {
 
+// launch shape: persistent CTAs of HMRM_LIN_THREADS threads, HMRM_LIN_CTAS of them per SM
+#ifndef HMRM_LIN_THREADS
+#define HMRM_LIN_THREADS 256
+#endif
+#ifndef HMRM_LIN_CTAS
+#define HMRM_LIN_CTAS 4
+#endif
+
 #define HMRM_LIN_FRAC 16
 #define HMRM_LIN_PERIOD 65536u      // samples between exact re-anchors (keeps the error bound of fact 4)
 #define HMRM_LIN_MARGIN 4         // x, y: fixed-point units
@@ -335,7 +343,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 }
 
 template <bool kStats, bool kFast>
-__global__ void __launch_bounds__(256, 4) k2_render_lin(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin(const __grid_constant__ RenderParams P) {
 	const int lane = threadIdx.x & 31;
 	const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
 
