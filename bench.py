@@ -196,7 +196,7 @@ def reference_arm(args, wl) -> None:
     }
     if res["ms_as_shipped"]:
         line["cpu_baseline"]["value_as_shipped"] = rays * len(res["ms_as_shipped"]) / (sum(res["ms_as_shipped"]) * 1e-3) / 1e6
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -461,14 +461,37 @@ def ours_arm(args, wl) -> None:
                 ok = ok and bool(np.array_equal(got, want))
             cb["parity_of_sample"] = "bit-exact" if ok else "MISMATCH"
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        emit(line)
 
     r.close()
     if dist is not None:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner there) must not add
+    lines: keep the real stdout for emit() and point fd 1 at stderr for everything else."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main() -> None:
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=12)
