@@ -324,3 +324,42 @@ def test_interleaved_bands_compose_full_frame(hmrm, renderer, oracle, world):
         assert not local.cpu().numpy()[mask].any()
     got = out.view(T * 4, W, 4)[:Hh].cpu().numpy()
     assert np.array_equal(got, full)
+
+
+@pytest.mark.parametrize("workload,frame_no", [("flythrough4k", 7), ("spherical1080", 31), ("ortho4k", 3), ("bands8k", 100)])
+def test_baseline_full_size_traversals_agree(hmrm, workload, frame_no):
+    """BASELINE.json's full sizes (16384^2 at 4K, 8192^2 ortho with step_dist/8, 32768^2 at 8K), bench.py's own
+    cameras: the reference loop as written (BRUTE) and both skip traversals give the same frame, the same per-pixel
+    first-hit sample index and the same reference-equivalent step totals.  (bench.py pins the same workload against
+    the unmodified reference on a 1/16 sample of the rays: cpu_baseline.parity_of_sample.)"""
+    import importlib.util
+    from pathlib import Path
+
+    spec = importlib.util.spec_from_file_location("hmrm_bench", Path(__file__).resolve().parent.parent / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    wl = bench.WORKLOADS[workload]
+    r = hmrm.Renderer(0)
+    try:
+        r.min_height, r.max_height = bench.MIN_HEIGHT, bench.MAX_HEIGHT
+        r.synth_maps(wl["log2n"], bench.SEED)
+        c = bench.camera(wl, frame_no)
+        common = dict(projection=wl["projection"], screen_width=wl["W"], screen_height=wl["H"], cam_pos=c["pos"],
+                      hang=hmrm.deg2rad(c["hang_deg"]), vang=hmrm.deg2rad(c["vang_deg"]), hfov=hmrm.deg2rad(c["hfov_deg"]),
+                      ortho_width=c["ortho_width"], grid_width=bench.GRID_WIDTH, step_dist=wl["step_dist"],
+                      flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX)
+        got = []
+        for trav in TRAVERSALS:
+            f = r.frame(traversal=trav, **common)
+            fb = r.render(f).copy()
+            st = r.stats()
+            got.append((fb, r.step_index(f).copy(), (st.rays, st.box_hits, st.surf_hits, st.steps, st.max_steps), st.status))
+        base = got[0]
+        assert base[3] == 0 and base[2][0] == wl["W"] * wl["H"] and base[2][2] > 0
+        assert (base[0][..., 3] == 255).all()
+        for other in got[1:]:
+            assert np.array_equal(base[0], other[0])
+            assert np.array_equal(base[1], other[1])
+            assert base[2] == other[2] and other[3] == 0
+    finally:
+        r.close()
