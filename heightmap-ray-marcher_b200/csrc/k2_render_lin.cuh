@@ -21,8 +21,10 @@
 //     q +- 1/2, so with HMRM_LIN_ZMARGIN = 8 + 2 sixteenths:
 //       * above the (dilated) block max q  when Z_j > 16 q + 10  (q < 65535: clamped values never prove anything),
 //       * hit                              when Z_j < 16 q - 10  (q > 0; same monotone Zq16 argument as k2_render_skip.cuh),
-//       * a jump of m samples              when samples n and n+m are both >= 4 units inside the cleared
-//                                          neighbourhood and the grid, and both are above q: V is monotone in j.
+//       * a jump of m samples              when m |D| / 2^16 <= (room to the edge of the cleared neighbourhood) - 4 - 1
+//                                          per axis and <= (Z_j - 16 q - 10) - 2 in height: the model itself is
+//                                          integer-exact (V_{j+m} - V_j is within 1 unit of m D / 2^16, V is monotone
+//                                          in j), so the end point needs no test.
 //     Any sample that is NOT decided with that margin is handed to resolve_exact(): the exact FP64 position P_n is
 //     reconstructed from the last exact anchor with the binade-aware closed form (fact 1) and the reference's own
 //     expressions (divide, truncate, compare with the FP64 surface) decide it.  On the bench frame that happens
@@ -153,7 +155,8 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 	const float inv_adz = fast_rcp(adz);
 	const int cell_exit = (int)fminf(P.cell_exit_scale * adz + 512.0f, 1.0e9f);
 	const long long grid_vx = (long long)P.map_w << k, grid_vy = (long long)P.map_h << k;   // <= 2^30
-	const unsigned span_x = (unsigned)(grid_vx - 2 * HMRM_LIN_MARGIN), span_y = (unsigned)(grid_vy - 2 * HMRM_LIN_MARGIN);
+	const unsigned grid_ux = (unsigned)grid_vx, grid_uy = (unsigned)grid_vy;
+	const unsigned span_x = grid_ux - 2u * HMRM_LIN_MARGIN, span_y = grid_uy - 2u * HMRM_LIN_MARGIN;
 	const int cell_mask = (1 << k) - 1;
 	int level = P.lstart;
 
@@ -213,23 +216,19 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		}
 
 		unsigned m = 1u;
-		bool carried = false;      // wx/wy/wz already hold sample n+m
 		if (!exact && above(vz, q)) {
 			// above every surface value of the neighbourhood (or of the cell): this sample cannot hit
 			if (level > 0) {
 				float est_xy, est_z;
-				int lo_x, hi_x, lo_y, hi_y;
 				for (;;) {
-					const int sh = k + level;
-					const int bx = vx >> sh, by = vy >> sh;
-					lo_x = (max(bx - 1, 0) << sh) + HMRM_LIN_MARGIN;
-					lo_y = (max(by - 1, 0) << sh) + HMRM_LIN_MARGIN;
-					hi_x = (int)min((long long)(bx + 2) << sh, grid_vx) - HMRM_LIN_MARGIN;
-					hi_y = (int)min((long long)(by + 2) << sh, grid_vy) - HMRM_LIN_MARGIN;
-					const float ex_ = __int2float_rz(lx.d >= 0 ? hi_x - vx : vx - lo_x) * inv_adx;
-					const float ey_ = __int2float_rz(ly.d >= 0 ? hi_y - vy : vy - lo_y) * inv_ady;
-					est_xy = fminf(ex_, ey_);
-					est_z = lz.d < 0 ? __int2float_rz(vz - (q << 4) - HMRM_LIN_ZMARGIN) * inv_adz : 3.0e38f;
+					// room (units) along the direction of motion inside the 3x3 neighbourhood of blocks, clipped to the grid
+					const unsigned w = 1u << (k + level), mask = w - 1u;
+					const unsigned ux = (unsigned)vx, uy = (unsigned)vy;
+					const int room_x = (int)(lx.d >= 0 ? min((ux | mask) + 1u + w, grid_ux) - ux : min((ux & mask) + w, ux));
+					const int room_y = (int)(ly.d >= 0 ? min((uy | mask) + 1u + w, grid_uy) - uy : min((uy & mask) + w, uy));
+					est_xy = fminf(__int2float_rz(room_x - (HMRM_LIN_MARGIN + 1)) * inv_adx,
+					               __int2float_rz(room_y - (HMRM_LIN_MARGIN + 1)) * inv_ady);
+					est_z = lz.d < 0 ? __int2float_rz(vz - (q << 4) - (HMRM_LIN_ZMARGIN + 2)) * inv_adz : 3.0e38f;
 					// climb while z leaves room for (much) wider blocks and the wider neighbourhood is cleared too
 					if (!(est_z >= 4.0f * est_xy) || level + P.lstride > P.ltop) break;
 					const int q2 = probe(level + P.lstride, vx, vy);
@@ -238,21 +237,12 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 					level += P.lstride;
 					q = q2;
 				}
+				// Jump length.  The model is integer-exact: V_{j+m} - V_j = round((j+m) D / 2^16) - round(j D / 2^16) lies
+				// within 1 unit of m D / 2^16 and V is monotone in j, so any m with m |D| / 2^16 <= room - margin - 1 per
+				// axis keeps samples n .. n+m inside the cleared neighbourhood (and above q): no end-point test is needed.
+				// The float estimate errs low: conversions round toward zero, and 0.999 covers the ~2^-21 of the reciprocals.
 				const float est = fminf(fminf(est_xy, est_z), (float)(HMRM_LIN_PERIOD - j)) * 0.999f;
 				m = (est >= 2.0f) ? (unsigned)__float2int_rz(est) : 1u;
-				// samples n .. n+m-1 are skipped: sample n+m (examined next) must still be inside the cleared region
-				const long long qz = (long long)((q << 4) + HMRM_LIN_ZMARGIN);
-				while (m >= 2u) {
-					const long long ux = lin_at(lx, j + m), uy = lin_at(ly, j + m), uz = lin_at(lz, j + m);
-					if (ux >= lo_x && ux < hi_x && uy >= lo_y && uy < hi_y && uz > qz) {
-						wx = ux; wy = uy; wz = uz;
-						carried = true;
-						break;
-					}
-					if (kStats) tally.dbg[6] += 1u;
-					m -= 1u + (m >> 3);
-				}
-				if (m < 1u) m = 1u;
 				if (kStats) {
 					if (m >= 2u) { tally.dbg[0] += 1u; tally.dbg[1] += m; }
 					else tally.dbg[2] += 1u;
@@ -298,7 +288,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			level = 0;
 		}
 		n += m;
-		if (!carried) {
+		{
 			const unsigned jn = n - base;
 			wx = lin_at(lx, jn); wy = lin_at(ly, jn); wz = lin_at(lz, jn);
 		}
