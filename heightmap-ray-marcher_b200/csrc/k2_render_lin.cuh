@@ -181,6 +181,10 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			wx = lin_at(lx, 0u); wy = lin_at(ly, 0u); wz = lin_at(lz, 0u);
 		}
 		const unsigned j = n - base;
+		if (kStats) {                        // [6]: warp-level iterations (lane utilisation = lane iterations / 32 / this)
+			const unsigned am = __activemask();
+			if ((threadIdx.x & 31) == __ffs(am) - 1) tally.dbg[6] += 1u;
+		}
 		// does this sample need the exact treatment?  (within the margin of the grid edge; at level 0 also of a cell edge)
 		bool exact = false;
 		// (grid extents are <= 2^30 units, so "inside by the margin" is a 32-bit statement once the high words are zero)
