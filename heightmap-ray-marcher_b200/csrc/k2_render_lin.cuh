@@ -108,7 +108,7 @@ __device__ __forceinline__ bool lin_slope(double s_units, long long &d) {
 
 template <bool kStats>
 __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray, double ex, double ey, double ez,
-                                          uint32_t &rgba, bool &real_hit, int &first_hit, PixelTally &tally) {
+                                          unsigned &hit_cell, bool &real_hit, int &first_hit, PixelTally &tally) {
 	const int k = P.fx_bits;
 	// exact state: the anchor sample and the reference's per-step addend
 	AxisState ax, ay, az;
@@ -263,7 +263,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			// level 0, cell known, clearly below the surface: the reference's test `z < surf` holds (main/hmap.cpp:1016)
 			const size_t cell = (size_t)(vx >> k) + (size_t)(vy >> k) * (size_t)P.map_w;
 			if (kStats) tally.dbg[5] += 1u;
-			rgba = hit_colour(P, __ldg(P.color + cell));
+			hit_cell = (unsigned)cell;      // colour fetched by the caller, once the whole warp is out of the loop
 			real_hit = true;
 			first_hit = (n > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)n;
 			n += 1u;
@@ -282,7 +282,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			const size_t cell = (size_t)gx + (size_t)gy * (size_t)P.map_w;
 			if (kStats) fetches += 1u;
 			if (az.p < __ldg(P.surf + cell)) {
-				rgba = hit_colour(P, __ldg(P.color + cell));
+				hit_cell = (unsigned)cell;      // colour fetched by the caller, once the whole warp is out of the loop
 				real_hit = true;
 				first_hit = (n > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)n;
 				n += 1u;
@@ -316,7 +316,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			kk += 1ULL;
 			if (kStats) fetches += 1u;
 			if (az.p < __ldg(P.surf + cell)) {
-				rgba = hit_colour(P, __ldg(P.color + cell));
+				hit_cell = (unsigned)cell;      // colour fetched by the caller, once the whole warp is out of the loop
 				real_hit = true;
 				first_hit = (kk - 1ULL > 0x7FFFFFFFULL) ? 0x7FFFFFFF : (int)(kk - 1ULL);
 				break;
@@ -345,6 +345,8 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin
 	// wide grab that swallows several heavy tiles doubles the frame time), but the tile rows the host has placed at
 	// the end of the schedule because they look above the horizon are grabbed 8 tiles at a time: a sky tile costs
 	// ~25 ns of SM time and a frame's worth of them is otherwise bound by the single-address atomic.
+	// (Issuing the next grab before the current tile is processed hides the atomic's round trip but makes every warp
+	// sit on a reserved tile: measured 0.53 -> 0.56 ms on the bench frame, dropped.)
 	unsigned cur = 0u, end = 0u;
 	for (;;) {
 		if (cur == end) {
@@ -369,16 +371,20 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin
 			uint32_t rgba = 0u;
 			bool real_hit = false;
 			int first_hit = -1;
+			unsigned hit_cell = 0u;
 			if (!(kFast && fast_miss(P, px, py, rgba))) {
 				const Ray ray = generate_ray(P, px, py);
 				double ex, ey, ez;
 				if (box_entry(P, ray, ex, ey, ez)) {
 					tally.box_hit = 1u;
 					first_hit = -2;
-					march_lin<kStats>(P, ray, ex, ey, ez, rgba, real_hit, first_hit, tally);
+					march_lin<kStats>(P, ray, ex, ey, ez, hit_cell, real_hit, first_hit, tally);
 				}
 				if (!real_hit) rgba = miss_colour(P, ray.dz);
-				else tally.surf_hit = 1u;
+				else {
+					rgba = hit_colour(P, __ldg(P.color + hit_cell));
+					tally.surf_hit = 1u;
+				}
 			}
 			P.fb[(size_t)py * (size_t)P.W + (size_t)px] = rgba;
 			if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
