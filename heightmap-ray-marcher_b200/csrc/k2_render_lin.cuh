@@ -346,7 +346,9 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin
 	// the end of the schedule because they look above the horizon are grabbed 8 tiles at a time: a sky tile costs
 	// ~25 ns of SM time and a frame's worth of them is otherwise bound by the single-address atomic.
 	// (Issuing the next grab before the current tile is processed hides the atomic's round trip but makes every warp
-	// sit on a reserved tile: measured 0.53 -> 0.56 ms on the bench frame, dropped.)
+	// sit on a reserved tile: measured 0.53 -> 0.56 ms on the bench frame, dropped.  A CTA-level pool in shared memory
+	// refilled with one global atomic per 4/8/16 tiles changed nothing, 0.526 vs 0.528 ms: the wait on the atomic shows
+	// in the stall samples but other warps fill the issue slots.)
 	unsigned cur = 0u, end = 0u;
 	for (;;) {
 		if (cur == end) {
