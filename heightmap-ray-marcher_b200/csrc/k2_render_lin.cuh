@@ -92,11 +92,13 @@ __device__ __noinline__ void advance_exact(AxisState &ax, AxisState &ay, AxisSta
 
 struct LinAxis {
 	long long d;     // per-step motion in units * 2^16
-	int v0;          // position of the base sample in units
+	long long a0;    // V_0 * 2^16 + 2^15: position of the base sample, pre-shifted, with the rounding half added
 };
 
-__device__ __forceinline__ long long lin_at(const LinAxis &l, unsigned j) {
-	return (long long)l.v0 + (((long long)j * l.d + (1LL << (HMRM_LIN_FRAC - 1))) >> HMRM_LIN_FRAC);
+// 2^16 V_j + (fraction): V_j = V_0 + round(j D / 2^16) is the arithmetic shift of this by 16.  One IMAD.WIDE (the
+// 64-bit addend is free) and one IMAD; |a0| < 2^47 + 2^15 and j |D| < 2^17 * 2^42, so it cannot wrap.
+__device__ __forceinline__ long long lin_acc(const LinAxis &l, unsigned j) {
+	return l.a0 + (long long)((unsigned long long)j * (unsigned long long)l.d);
 }
 
 // slope of one axis of the integer model; false if it does not fit (|motion| >= 2^26 units per step, NaN)
@@ -141,7 +143,9 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		const bool okx = magic_decode(__fma_rn(ax.p, P.fx_scale, HMRM_MAGIC), vx);
 		const bool oky = magic_decode(__fma_rn(ay.p, -P.fx_scale, HMRM_MAGIC), vy);
 		const bool okz = magic_decode(__fma_rn(az.p, zs16, zo16), vz);
-		lx.v0 = vx; ly.v0 = vy; lz.v0 = vz;
+		lx.a0 = ((long long)vx << HMRM_LIN_FRAC) + (1LL << (HMRM_LIN_FRAC - 1));
+		ly.a0 = ((long long)vy << HMRM_LIN_FRAC) + (1LL << (HMRM_LIN_FRAC - 1));
+		lz.a0 = ((long long)vz << HMRM_LIN_FRAC) + (1LL << (HMRM_LIN_FRAC - 1));
 		return okx && oky && okz;
 	};
 	unsigned base = 0u;       // sample index of V_0
@@ -168,7 +172,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 	// `above q` / `below q` with the model's error (< 1.6/16 Zq) and Zq16's rounding (ties at q +- 1/2) covered
 	auto above = [&](int vz, int q) -> bool { return vz > (q << 4) + HMRM_LIN_ZMARGIN && q < 65535; };
 
-	long long wx = lin_at(lx, 0u), wy = lin_at(ly, 0u), wz = lin_at(lz, 0u);   // model position of sample n
+	long long wx = lin_acc(lx, 0u), wy = lin_acc(ly, 0u), wz = lin_acc(lz, 0u);   // model position of sample n, * 2^16
 	for (;;) {
 		// keep the error bound: re-anchor the model on an exact position every HMRM_LIN_PERIOD samples
 		if (n - base >= HMRM_LIN_PERIOD) {
@@ -178,7 +182,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 				model = false;
 				break;
 			}
-			wx = lin_at(lx, 0u); wy = lin_at(ly, 0u); wz = lin_at(lz, 0u);
+			wx = lin_acc(lx, 0u); wy = lin_acc(ly, 0u); wz = lin_acc(lz, 0u);
 		}
 		const unsigned j = n - base;
 		if (kStats) {                        // [6]: warp-level iterations (lane utilisation = lane iterations / 32 / this)
@@ -187,21 +191,27 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		}
 		// does this sample need the exact treatment?  (within the margin of the grid edge; at level 0 also of a cell edge)
 		bool exact = false;
-		// (grid extents are <= 2^30 units, so "inside by the margin" is a 32-bit statement once the high words are zero)
-		const bool inside = ((unsigned)((unsigned long long)wx >> 32) | (unsigned)((unsigned long long)wy >> 32)) == 0u &&
-		                    (unsigned)wx - (unsigned)HMRM_LIN_MARGIN < span_x && (unsigned)wy - (unsigned)HMRM_LIN_MARGIN < span_y;
+		// V = w >> 16.  It is a non-negative 32-bit number iff the high word of w is in [0, 2^16); the grid extents are
+		// <= 2^30 units, so "inside by the margin" is then a 32-bit statement.
+		const int vx = (int)(wx >> HMRM_LIN_FRAC), vy = (int)(wy >> HMRM_LIN_FRAC);      // low 32 bits: one funnel shift
+		const bool inside = ((unsigned)((unsigned long long)wx >> 32) | (unsigned)((unsigned long long)wy >> 32)) < 65536u &&
+		                    (unsigned)vx - (unsigned)HMRM_LIN_MARGIN < span_x && (unsigned)vy - (unsigned)HMRM_LIN_MARGIN < span_y;
 		if (!inside) {
 			// Certainly outside the grid (main/hmap.cpp:1006-1011)?  The reference truncates toward zero (:1001-1004), so
 			// coordinates in (-1, 0) cells still map to cell 0: the low edge of the grid is at -1 cell, not at 0.
+			const long long fx = wx >> HMRM_LIN_FRAC, fy = wy >> HMRM_LIN_FRAC;
 			const long long low_edge = -(1LL << k) - HMRM_LIN_MARGIN;
-			if (wx < low_edge || wy < low_edge || wx >= grid_vx + HMRM_LIN_MARGIN || wy >= grid_vy + HMRM_LIN_MARGIN) {
+			if (fx < low_edge || fy < low_edge || fx >= grid_vx + HMRM_LIN_MARGIN || fy >= grid_vy + HMRM_LIN_MARGIN) {
 				finished = true;
 				break;
 			}
 			exact = true;         // (the whole (-1, 0] strip of the truncation quirk goes the exact way too)
 		}
-		const int vx = (int)wx, vy = (int)wy;
-		const int vz = (int)(wz < -1073741824LL ? -1073741824LL : (wz > 1073741824LL ? 1073741824LL : wz));
+		// height: the shifted value fits 32 bits iff the high word is in [-2^15, 2^15); otherwise it is far above or far
+		// below everything the 16-bit pyramid can hold
+		const int wz_hi = (int)(wz >> 32);
+		int vz = (int)(wz >> HMRM_LIN_FRAC);
+		if ((unsigned)(wz_hi + 32768) >= 65536u) vz = wz_hi < 0 ? -1073741824 : 1073741824;
 
 		int q = 0;
 		if (!exact) {
@@ -294,7 +304,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		n += m;
 		{
 			const unsigned jn = n - base;
-			wx = lin_at(lx, jn); wy = lin_at(ly, jn); wz = lin_at(lz, jn);
+			wx = lin_acc(lx, jn); wy = lin_acc(ly, jn); wz = lin_acc(lz, jn);
 		}
 		if (n >= 0x7FF00000u) {          // ~2^31 samples: give up like a hang would, but flagged
 			tally.cut_off = 1u;
