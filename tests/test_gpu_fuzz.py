@@ -180,3 +180,35 @@ def test_long_grazing_marches_match_oracle(hmrm, renderer, oracle, seed):
     st = check_against_oracle(hmrm, renderer, oracle, hm, cm, (0.299, 0.587, 0.114), 0.0, mx, fk, f"seed {seed} {fk}")
     assert st[0].max_steps > 100, st[0].max_steps
     assert st[1].fetches < st[0].fetches          # the skip traversal really skipped
+
+
+@pytest.mark.parametrize("case", range(6))
+def test_rays_longer_than_the_model_period_match_oracle(hmrm, renderer, oracle, case):
+    """Steps of 1/4000 .. 1/700 of a cell: hundreds of thousands of samples per ray, so the integer model of
+    k2_render_lin is re-anchored on an exact position several times per ray (HMRM_LIN_PERIOD = 65536 samples) and the
+    FP64 skip kernel crosses many binades.  A handful of rays, every one checked against the oracle."""
+    rng = np.random.RandomState(7700 + case)
+    n = [96, 128, 160, 64, 200, 100][case]
+    yy, xx = np.mgrid[0:n, 0:n]
+    if case % 3 == 0:
+        v = np.full((n, n), 30.0)
+        v[:, n // 2: n // 2 + 3] = 220                       # a wall far from the entry edge
+    elif case % 3 == 1:
+        v = (np.sin(xx / 11.0) * np.cos(yy / 17.0) * 60 + 90).clip(0, 255)
+    else:
+        v = (xx * 200.0 / (n - 1))
+    hm = np.dstack([v, v, v]).astype(np.uint8)
+    cm = rng.randint(0, 256, size=(n, n, 4)).astype(np.uint8)
+    gw = [0.01, 0.05, 0.0078125, 1.0, 0.02, 0.3][case]
+    ext = n * gw
+    mx = 0.25 * ext
+    step = gw / [2000.0, 700.0, 1200.0, 4000.0, 1500.0, 2500.0][case]
+    height = mx * 1.05
+    pos = (-0.05 * ext, -0.45 * ext, height)
+    target = (0.9 * ext, -0.55 * ext, 0.1 * mx)
+    d = np.array([target[0] - pos[0], target[1] - pos[1], target[2] - pos[2]])
+    fk = dict(projection=1 + case % 3, screen_width=4, screen_height=3, cam_pos=pos,
+              hang=float(np.arctan2(d[1], d[0])), vang=float(np.arccos(d[2] / np.linalg.norm(d))), hfov=0.2,
+              ortho_width=float(ext / 40), grid_width=gw, step_dist=step, bg=(9, 8, 7))
+    st = check_against_oracle(hmrm, renderer, oracle, hm, cm, (0.299, 0.587, 0.114), 0.0, mx, fk, f"case {case} {fk}")
+    assert st[0].max_steps > 66000, st[0].max_steps
