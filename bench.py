@@ -329,7 +329,8 @@ def ours_arm(args, wl) -> None:
     # ---- e2e: the user's call — host output buffer, D2H inside the timed region ----
     h_out_t = torch.from_numpy(h_out)          # same pinned memory, as a tensor (for the gathered frame)
 
-    host_bufs = [h_out, binding.pinned_empty((H, W, 4)), binding.pinned_empty((H, W, 4))]
+    E2E_DEPTH = 3                               # frames that may stay in flight behind the newest one
+    host_bufs = [h_out] + [binding.pinned_empty((H, W, 4)) for _ in range(E2E_DEPTH)]
 
     def e2e_step(i: int, n: int) -> None:
         if bands and world > 1:
@@ -338,10 +339,10 @@ def ours_arm(args, wl) -> None:
                 h_out_t.copy_(full, non_blocking=True)
             stream.synchronize()
         else:
-            # the library's streaming call: frames i and i-1 render while frame i-2 is still being copied to the
-            # host; after wait_pending(2) frame i-2 is complete in its host buffer (three buffers rotate)
-            r.render_async(frame_of(n), host_bufs[i % 3])
-            r.wait_pending(2)
+            # the library's streaming call: the newest frames render while an older one is still being copied to the
+            # host; after wait_pending(d) frame i-d is complete in its host buffer (d + 1 buffers rotate)
+            r.render_async(frame_of(n), host_bufs[i % (E2E_DEPTH + 1)])
+            r.wait_pending(E2E_DEPTH)
 
     for i, n in enumerate(warm_frames):
         e2e_step(i, n)
@@ -438,9 +439,9 @@ def ours_arm(args, wl) -> None:
                          "note": "algorithmic bytes = 8*S + 4*hits + 4*W*H with S = reference-equivalent steps"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": W * H * 4,
-                    "api": "hmrm_render_async + hmrm_wait_pending(2): every frame lands in pinned host memory; the "
-                           "copy-out of frame n overlaps the kernels of frames n+1 and n+2 (three device + three "
-                           "host buffers)"},
+                    "api": "hmrm_render_async + hmrm_wait_pending(3): every frame lands in pinned host memory; the "
+                           "copy-out of frame n overlaps the kernels of the next frames (four device + four host "
+                           "buffers)"},
             "gpu_launches": launches,
             "clocks": clocks,
         }

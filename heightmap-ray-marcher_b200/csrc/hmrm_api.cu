@@ -32,8 +32,8 @@ namespace {
 
 std::string g_create_error;
 
-const int kLaunchSlots = 4;
-const int kFrameRing = 3;      // device frame buffers (and compute streams) whole frames rotate through
+const int kLaunchSlots = 6;
+const int kFrameRing = 4;      // device frame buffers (and compute streams) whole frames rotate through
 
 // Everything one launch writes before / while its kernel runs.  A slot is reused only after the kernel that used
 // it last has finished (ev_end), so up to kLaunchSlots frames of one context may be in flight on any streams.

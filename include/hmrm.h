@@ -122,8 +122,8 @@ int hmrm_render_device(hmrm_ctx *ctx, const hmrm_frame *f, void *d_rgba_out, voi
  * asynchronously; hmrm_wait() joins.  Used for frame sharding (one frame in flight per context). */
 int hmrm_render_async(hmrm_ctx *ctx, const hmrm_frame *f, uint8_t *rgba_out);
 int hmrm_wait(hmrm_ctx *ctx);
-/* Streaming: up to three whole frames (cycle_period 1) may be in flight; the copy-out of one overlaps the kernels
- * of the next two.  hmrm_wait_pending(ctx, n) (n = 1 or 2) returns when every frame but the n most recent is complete
+/* Streaming: up to four whole frames (cycle_period 1) may be in flight; the copy-out of one overlaps the kernels
+ * of the next ones.  hmrm_wait_pending(ctx, n) (n = 1..3) returns when every frame but the n most recent is complete
  * in its host buffer (so n + 1 host buffers are rotated); hmrm_wait_pending(ctx, 0) == hmrm_wait. */
 int hmrm_wait_pending(hmrm_ctx *ctx, int max_pending);
 

@@ -137,7 +137,7 @@ def test_render_device_and_async_paths_agree(hmrm, renderer, oracle):
     assert np.array_equal(pinned, want)
 
 
-@pytest.mark.parametrize("depth", [1, 2])
+@pytest.mark.parametrize("depth", [1, 2, 3])
 def test_streaming_async_frames_equal_synchronous_frames(hmrm, renderer, oracle, depth):
     """hmrm_render_async + hmrm_wait_pending(depth): depth+1 frames in flight (copy-out overlaps the next kernels)."""
     from heightmap_ray_marcher_b200 import binding
