@@ -472,6 +472,12 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		while ((1 << clog) < dim) clog += 1;
 		P.fx_bits = 30 - clog < 20 ? 30 - clog : 20;
 		P.fx_scale = std::ldexp(1.0, P.fx_bits) / f->grid_width;
+		if (P.fx_bits >= 1) {
+			P.lin_grid_x = (unsigned)c->map_w << P.fx_bits;
+			P.lin_grid_y = (unsigned)c->map_h << P.fx_bits;
+			P.lin_span_x = P.lin_grid_x - 2u * HMRM_LIN_MARGIN;
+			P.lin_span_y = P.lin_grid_y - 2u * HMRM_LIN_MARGIN;
+		}
 		P.zq_scale = c->zq_scale;
 		P.zq_offset = c->zq_offset;
 		P.ltop = c->mip_levels - 1;

@@ -158,9 +158,6 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 	const float adz = fabsf((float)lz.d) * (1.0f / 65536.0f);
 	const float inv_adz = fast_rcp(adz);
 	const int cell_exit = (int)fminf(P.cell_exit_scale * adz + 512.0f, 1.0e9f);
-	const long long grid_vx = (long long)P.map_w << k, grid_vy = (long long)P.map_h << k;   // <= 2^30
-	const unsigned grid_ux = (unsigned)grid_vx, grid_uy = (unsigned)grid_vy;
-	const unsigned span_x = grid_ux - 2u * HMRM_LIN_MARGIN, span_y = grid_uy - 2u * HMRM_LIN_MARGIN;
 	const int cell_mask = (1 << k) - 1;
 	int level = P.lstart;
 
@@ -195,13 +192,14 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		// <= 2^30 units, so "inside by the margin" is then a 32-bit statement.
 		const int vx = (int)(wx >> HMRM_LIN_FRAC), vy = (int)(wy >> HMRM_LIN_FRAC);      // low 32 bits: one funnel shift
 		const bool inside = ((unsigned)((unsigned long long)wx >> 32) | (unsigned)((unsigned long long)wy >> 32)) < 65536u &&
-		                    (unsigned)vx - (unsigned)HMRM_LIN_MARGIN < span_x && (unsigned)vy - (unsigned)HMRM_LIN_MARGIN < span_y;
+		                    (unsigned)vx - (unsigned)HMRM_LIN_MARGIN < P.lin_span_x && (unsigned)vy - (unsigned)HMRM_LIN_MARGIN < P.lin_span_y;
 		if (!inside) {
 			// Certainly outside the grid (main/hmap.cpp:1006-1011)?  The reference truncates toward zero (:1001-1004), so
 			// coordinates in (-1, 0) cells still map to cell 0: the low edge of the grid is at -1 cell, not at 0.
 			const long long fx = wx >> HMRM_LIN_FRAC, fy = wy >> HMRM_LIN_FRAC;
 			const long long low_edge = -(1LL << k) - HMRM_LIN_MARGIN;
-			if (fx < low_edge || fy < low_edge || fx >= grid_vx + HMRM_LIN_MARGIN || fy >= grid_vy + HMRM_LIN_MARGIN) {
+			if (fx < low_edge || fy < low_edge || fx >= (long long)P.lin_grid_x + HMRM_LIN_MARGIN ||
+			    fy >= (long long)P.lin_grid_y + HMRM_LIN_MARGIN) {
 				finished = true;
 				break;
 			}
@@ -238,8 +236,8 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 					// room (units) along the direction of motion inside the 3x3 neighbourhood of blocks, clipped to the grid
 					const unsigned w = 1u << (k + level), mask = w - 1u;
 					const unsigned ux = (unsigned)vx, uy = (unsigned)vy;
-					const int room_x = (int)(lx.d >= 0 ? min((ux | mask) + 1u + w, grid_ux) - ux : min((ux & mask) + w, ux));
-					const int room_y = (int)(ly.d >= 0 ? min((uy | mask) + 1u + w, grid_uy) - uy : min((uy & mask) + w, uy));
+					const int room_x = (int)(lx.d >= 0 ? min((ux | mask) + 1u + w, P.lin_grid_x) - ux : min((ux & mask) + w, ux));
+					const int room_y = (int)(ly.d >= 0 ? min((uy | mask) + 1u + w, P.lin_grid_y) - uy : min((uy & mask) + w, uy));
 					est_xy = fminf(__int2float_rz(room_x - (HMRM_LIN_MARGIN + 1)) * inv_adx,
 					               __int2float_rz(room_y - (HMRM_LIN_MARGIN + 1)) * inv_ady);
 					est_z = lz.d < 0 ? __int2float_rz(vz - (q << 4) - (HMRM_LIN_ZMARGIN + 2)) * inv_adz : 3.0e38f;

@@ -30,6 +30,9 @@ struct RenderParams {
 	int tile_y_first, tile_y_step; // launch tile row t is frame tile row tile_y_first + t * tile_y_step (row interleave)
 	const int *row_order;          // optional permutation of the launch tile rows: expensive (grazing) rows first
 	unsigned batch_from_tile;      // tiles from this queue position on look above the horizon: grabbed 8 at a time
+	// k2_render_lin: grid extents in fixed-point units (map << fx_bits, <= 2^30) and the same minus twice the margin;
+	// host-computed so that the march loop reads them as constant-bank operands
+	unsigned lin_grid_x, lin_grid_y, lin_span_x, lin_span_y;
 	// map
 	int map_w, map_h;
 	// image plane (host-built, frame_setup.h)
