@@ -151,6 +151,17 @@ __global__ void __launch_bounds__(256) k1_build(const uint8_t *__restrict__ rgb8
 	const long long n_tiles = (long long)tiles_x * tiles_y;
 	const long long stride = (long long)gridDim.x * blockDim.x;
 	const bool vec = (w & 3) == 0;     // rows are 4-byte aligned in rgb8, 8-byte in lv0, 32-byte in surf
+	// Grey cells (R == G == B: every greyscale image after stb's channel replication, vendor/stb_image.h:1758) take
+	// their height from a 256-entry table built by the same expressions: bit-identical, and it removes the IEEE divide
+	// and ~60 other instructions per cell, which is what bounds this kernel (ncu: issue-active 66 %, DRAM 62 %).
+	__shared__ double s_grey[256];
+	__shared__ unsigned short z_grey[256];
+	for (int v = threadIdx.x; v < 256; v += blockDim.x) {
+		const double sv = fadd(height_of(q, (uint32_t)v, (uint32_t)v, (uint32_t)v), q.min_height);
+		s_grey[v] = sv;
+		z_grey[v] = (unsigned short)zq16(sv, zq_scale, zq_offset);
+	}
+	__syncthreads();
 	for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_tiles; t += stride) {
 		const int bx = (int)(t % tiles_x), by = (int)(t / tiles_x);
 		const int x0 = bx * 4, y0 = by * 4;
@@ -179,10 +190,24 @@ __global__ void __launch_bounds__(256) k1_build(const uint8_t *__restrict__ rgb8
 			}
 			double s[4];
 			int zq[4];
+			const bool grey = r[0] == g[0] && g[0] == b[0] && r[1] == g[1] && g[1] == b[1] &&
+			                  r[2] == g[2] && g[2] == b[2] && r[3] == g[3] && g[3] == b[3];
+			if (grey) {
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					s[i] = s_grey[r[i]];
+					zq[i] = (int)z_grey[r[i]];
+				}
+			}
+			else {
+#pragma unroll
+				for (int i = 0; i < 4; ++i) {
+					s[i] = fadd(height_of(q, r[i], g[i], b[i]), q.min_height);
+					zq[i] = zq16(s[i], zq_scale, zq_offset);
+				}
+			}
 #pragma unroll
 			for (int i = 0; i < 4; ++i) {
-				s[i] = fadd(height_of(q, r[i], g[i], b[i]), q.min_height);
-				zq[i] = zq16(s[i], zq_scale, zq_offset);
 				if (i < valid) m1[j >> 1][i >> 1] = max(m1[j >> 1][i >> 1], zq[i]);
 			}
 			if (vec) {
