@@ -22,8 +22,10 @@ def random_maps(rng, kind):
     else:
         h, w = int(rng.randint(20, 200)), int(rng.randint(20, 200))
     style = rng.randint(0, 4)
-    if style == 0:       # white noise: needles
+    if style == 0:       # white noise: needles; half of the cells grey (R == G == B: K1's table path), half coloured
         hm = rng.randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+        grey = rng.rand(h, w) < 0.5
+        hm[grey] = hm[grey][:, :1]
     elif style == 1:     # flat
         hm = np.full((h, w, 3), int(rng.randint(0, 256)), dtype=np.uint8)
     elif style == 2:     # smooth ramp + steps
