@@ -239,8 +239,18 @@ def ours_arm(args, wl) -> None:
                        step_dist=wl["step_dist"], traversal=traversal, flags=flags,
                        band_count=world if (bands and w == W) else 0, band_index=rank if (bands and w == W) else 0)
 
+    band_step = [0]
+
     def render_step(n: int, flags: int = 0):
-        """One step of the workload on this rank: a whole frame, or this rank's bands + the gather to rank 0."""
+        """One step of the workload on this rank: a whole frame, or this rank's bands of the frame everybody works on.
+        Bands land in rank 0's frame either by peer stores from the render kernel itself (default) or by pack +
+        NCCL gather + unpack (--exchange gather)."""
+        if bands and world > 1 and peer is not None:
+            i = band_step[0]
+            band_step[0] += 1
+            r.render_device(frame_of(n, flags=flags), peer.pointer(i), stream.cuda_stream)
+            peer.complete()
+            return peer.tensor(i)
         r.render_device(frame_of(n, flags=flags), d_out, stream.cuda_stream)
         if bands and world > 1:
             return MG.gather_interleaved_bands(d_out, H, rank, world)
@@ -266,6 +276,9 @@ def ours_arm(args, wl) -> None:
     h_out = binding.pinned_empty((H, W, 4))
     stream = torch.cuda.Stream(device=local)       # a real (non-default) stream: kernels and events share it
     torch.cuda.set_stream(stream)
+    peer = None
+    if bands and world > 1 and args.exchange == "peer":
+        peer = MG.PeerFrame(r, H, W, rank, world, local)
 
     # ---- untimed statistics pass over the timed frames: reference-equivalent steps S, hits, fetches ----
     S = hits = fetches = 0
@@ -424,8 +437,10 @@ def ours_arm(args, wl) -> None:
                        "precision": "fp64_exact",
                        "in_flight": "1 frame" if bands else f"{max(1, min(4, args.inflight))} frames on as many streams "
                                     "(the tail of frame n overlaps the head of frame n+1)",
-                       "sharding": (f"each frame split into interleaved 4-row tile bands over {world} GPU(s), RGBA8 bands "
-                                    "gathered to rank 0 (NCCL), maps replicated") if bands else
+                       "sharding": (f"each frame split into interleaved 4-row tile bands over {world} GPU(s), maps replicated; "
+                                    + ("every rank's kernel stores its bands straight into rank 0's frame (CUDA IPC peer "
+                                       "memory over NVLink), one-element all-reduce as the completion barrier"
+                                       if peer is not None else "RGBA8 bands packed, gathered to rank 0 (NCCL), unpacked")) if bands else
                                    f"frames round-robin over {world} GPU(s), maps replicated, no collective",
                        "l2": "inputs larger than L2 (2 GiB FP64 height plane + 1 GiB RGBA8 colormap per GPU; "
                              "the camera moves every frame)" if wl["log2n"] >= 13 else "inputs may fit L2; camera moves every frame"},
@@ -464,6 +479,8 @@ def ours_arm(args, wl) -> None:
             line["cpu_baseline"] = cb
         emit(line)
 
+    if peer is not None:
+        peer.close()
     r.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -501,6 +518,8 @@ def main() -> None:
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default="flythrough4k")
     ap.add_argument("--traversal", choices=["auto", "brute", "skip"], default="auto")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", choices=["peer", "gather"], default="peer",
+                    help="bands workloads at N > 1: how the bands reach rank 0")
     ap.add_argument("--cpu-frames", type=int, default=2)
     ap.add_argument("--inflight", type=int, default=2, help="frames in flight in the device-resident timing (1..4)")
     args = ap.parse_args()

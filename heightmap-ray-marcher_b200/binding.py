@@ -99,6 +99,11 @@ PROTOTYPES = {
                                C.POINTER(C.c_double)]),
     "hmrm_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "hmrm_host_free": (None, [C.c_void_p]),
+    "hmrm_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "hmrm_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hmrm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmrm_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "hmrm_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -303,6 +308,29 @@ class Renderer:
         out = (C.c_int64 * 12)()
         self._check(self._lib.hmrm_get_debug_counters(self._h, out))
         return list(out)
+
+    # ---- peer frames (one frame rendered by several GPUs, see include/hmrm.h) ----
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        self._check(self._lib.hmrm_device_alloc(self._h, nbytes, C.byref(p)))
+        return int(p.value)
+
+    def device_free(self, dptr: int) -> None:
+        self._check(self._lib.hmrm_device_free(self._h, C.c_void_p(dptr)))
+
+    def ipc_export(self, dptr: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self._check(self._lib.hmrm_ipc_export(self._h, C.c_void_p(dptr), buf))
+        return bytes(buf)
+
+    def ipc_open(self, handle: bytes) -> int:
+        buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+        p = C.c_void_p()
+        self._check(self._lib.hmrm_ipc_open(self._h, buf, C.byref(p)))
+        return int(p.value)
+
+    def ipc_close(self, dptr: int) -> None:
+        self._check(self._lib.hmrm_ipc_close(self._h, C.c_void_p(dptr)))
 
     def step_index(self, frame: Frame) -> np.ndarray:
         out = np.empty((frame.screen_height, frame.screen_width), dtype=np.int32)

@@ -1018,4 +1018,51 @@ void hmrm_host_free(void *ptr) {
 	if (ptr) cudaFreeHost(ptr);
 }
 
+int hmrm_device_alloc(hmrm_ctx *c, size_t bytes, void **dptr) {
+	if (!c || !dptr || bytes == 0) return c ? fail(c, HMRM_ERR_INVALID, "hmrm_device_alloc: bad arguments") : HMRM_ERR_INVALID;
+	*dptr = NULL;
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	HMRM_CUDA(c, cudaMalloc(dptr, bytes));
+	HMRM_CUDA(c, cudaMemset(*dptr, 0, bytes));
+	HMRM_CUDA(c, cudaDeviceSynchronize());
+	return HMRM_OK;
+}
+
+int hmrm_device_free(hmrm_ctx *c, void *dptr) {
+	if (!c) return HMRM_ERR_INVALID;
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	if (int rc = drain(c)) return rc;
+	if (dptr) HMRM_CUDA(c, cudaFree(dptr));
+	return HMRM_OK;
+}
+
+int hmrm_ipc_export(hmrm_ctx *c, void *dptr, uint8_t handle[HMRM_IPC_HANDLE_BYTES]) {
+	if (!c || !dptr || !handle) return c ? fail(c, HMRM_ERR_INVALID, "hmrm_ipc_export: bad arguments") : HMRM_ERR_INVALID;
+	static_assert(sizeof(cudaIpcMemHandle_t) == HMRM_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	cudaIpcMemHandle_t h;
+	HMRM_CUDA(c, cudaIpcGetMemHandle(&h, dptr));
+	std::memcpy(handle, &h, sizeof h);
+	return HMRM_OK;
+}
+
+int hmrm_ipc_open(hmrm_ctx *c, const uint8_t handle[HMRM_IPC_HANDLE_BYTES], void **dptr) {
+	if (!c || !dptr || !handle) return c ? fail(c, HMRM_ERR_INVALID, "hmrm_ipc_open: bad arguments") : HMRM_ERR_INVALID;
+	*dptr = NULL;
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	cudaIpcMemHandle_t h;
+	std::memcpy(&h, handle, sizeof h);
+	// maps the exporting device's memory into this process and enables peer access to it (NVLink / NVSwitch)
+	HMRM_CUDA(c, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return HMRM_OK;
+}
+
+int hmrm_ipc_close(hmrm_ctx *c, void *dptr) {
+	if (!c) return HMRM_ERR_INVALID;
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	if (int rc = drain(c)) return rc;
+	if (dptr) HMRM_CUDA(c, cudaIpcCloseMemHandle(dptr));
+	return HMRM_OK;
+}
+
 } // extern "C"

@@ -75,3 +75,88 @@ def gather_interleaved_bands(local_full, height: int, rank: int, world: int, dst
         n = len(range(r, T, world))
         full[r::world] = bufs[r][:n]
     return full.view(T * TILE_ROWS, local_full.shape[1], 4)[:height]
+
+
+class _DeviceBytes:
+    """CUDA array interface over a raw device pointer (so torch can view memory owned by libhmrm.so)."""
+
+    def __init__(self, ptr: int, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+class PeerFrame:
+    """One RGBA8 frame in the ROOT rank's device memory that every rank's kernel stores its tile rows into directly
+    (CUDA IPC mapping + peer stores over NVLink / NVSwitch, include/hmrm.h "peer frames").
+
+    Replaces pack -> NCCL gather -> unpack of `gather_interleaved_bands`: the exchange is fused into the render
+    kernel's own pixel stores, and the only collective left is a one-element all-reduce that tells the root the
+    frame is complete.  `buffers` frames rotate so that the root may still be reading frame n while frame n+1 is
+    being written (the root's read and its next barrier are ordered on one stream).
+    """
+
+    def __init__(self, renderer, height: int, width: int, rank: int, world: int, device: int, root: int = 0,
+                 buffers: int = 2, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.r, self.height, self.width = renderer, height, width
+        self.rank, self.world, self.root, self.group, self.device = rank, world, root, group, device
+        # NCCL: the completion barrier is stream-ordered on the GPU.  gloo (tests: several ranks on ONE GPU, which
+        # NCCL does not allow): host-side barrier after a stream synchronise.
+        self.on_host = world > 1 and dist.get_backend(group) != "nccl"
+        where = "cpu" if self.on_host else f"cuda:{device}"
+        nbytes = padded_height(height) * width * 4
+        self.ptrs = []
+        for _ in range(buffers):
+            if rank == root:
+                p = renderer.device_alloc(nbytes)
+                handle = torch.tensor(list(renderer.ipc_export(p)), dtype=torch.uint8, device=where)
+            else:
+                p = 0
+                handle = torch.empty(64, dtype=torch.uint8, device=where)
+            if world > 1:
+                dist.broadcast(handle, src=root, group=group)
+            if rank != root:
+                p = renderer.ipc_open(bytes(handle.cpu().tolist()))
+            self.ptrs.append(p)
+        self.token = torch.zeros(1, dtype=torch.float32, device=where)
+
+    def pointer(self, i: int) -> int:
+        """Device pointer (valid in THIS process) of buffer i mod buffers: pass it to Renderer.render_device."""
+        return self.ptrs[i % len(self.ptrs)]
+
+    def complete(self) -> None:
+        """Stream-ordered: once this has run on the root, every rank's stores of the frame rendered before it on the
+        current stream have landed in the root's buffer."""
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+
+            if self.on_host:
+                torch.cuda.current_stream().synchronize()
+            dist.all_reduce(self.token, group=self.group)
+
+    def tensor(self, i: int):
+        """Root only: torch uint8 view [height, W, 4] of buffer i mod buffers."""
+        import torch
+
+        if self.rank != self.root:
+            return None
+        full = torch.as_tensor(_DeviceBytes(self.pointer(i), (padded_height(self.height), self.width, 4)),
+                               device=f"cuda:{self.device}")
+        return full[: self.height]
+
+    def close(self) -> None:
+        import torch
+        import torch.distributed as dist
+
+        torch.cuda.synchronize()
+        if self.rank != self.root:
+            for p in self.ptrs:
+                self.r.ipc_close(p)
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        if self.rank == self.root:
+            for p in self.ptrs:
+                self.r.device_free(p)
+        self.ptrs = []

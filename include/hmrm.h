@@ -150,6 +150,19 @@ int hmrm_get_ray(const hmrm_frame *f, double w, double h, double pos[3], double 
 int hmrm_host_alloc(void **ptr, size_t bytes);
 void hmrm_host_free(void *ptr);
 
+/* ---- peer frames: one big frame rendered by several GPUs of one node (one process per GPU) ----
+ * The root rank allocates the frame on its device and exports a 64-byte handle (CUDA IPC); every other rank opens it
+ * and passes the mapped pointer to hmrm_render_device together with band_count / band_index: its kernel then stores
+ * its tile rows straight into the root's frame over NVLink — no pack, no gather, no unpack; the only collective left
+ * is the barrier that tells the root the frame is complete.  New surface: the reference has one OpenMP loop
+ * (main/hmap.cpp:978) and no multi-GPU path. */
+#define HMRM_IPC_HANDLE_BYTES 64
+int hmrm_device_alloc(hmrm_ctx *ctx, size_t bytes, void **dptr);          /* zero-filled */
+int hmrm_device_free(hmrm_ctx *ctx, void *dptr);
+int hmrm_ipc_export(hmrm_ctx *ctx, void *dptr, uint8_t handle[HMRM_IPC_HANDLE_BYTES]);   /* dptr from hmrm_device_alloc */
+int hmrm_ipc_open(hmrm_ctx *ctx, const uint8_t handle[HMRM_IPC_HANDLE_BYTES], void **dptr); /* in ANOTHER process */
+int hmrm_ipc_close(hmrm_ctx *ctx, void *dptr);
+
 #ifdef __cplusplus
 }
 #endif
