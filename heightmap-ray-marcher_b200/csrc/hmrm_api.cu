@@ -499,6 +499,8 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		P.lstart = lstart > P.ltop ? P.ltop : (lstart < lmin ? lmin : lstart);
 		if (P.fx_bits < 1) traversal = HMRM_TRAVERSAL_BRUTE;
 		P.lv = c->d_mip;
+		P.lv_total = (unsigned long long)(c->mip_offset[c->mip_levels - 1] +
+		                                  (size_t)c->mip_w[c->mip_levels - 1] * (size_t)c->mip_h[c->mip_levels - 1]);
 		for (int l = 0; l < 16; ++l) {
 			P.lv_desc[l].x = (l < c->mip_levels) ? (unsigned)c->mip_offset[l] : 0u;
 			P.lv_desc[l].y = (l < c->mip_levels) ? (unsigned)c->mip_w[l] : 0u;

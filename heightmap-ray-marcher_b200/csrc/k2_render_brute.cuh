@@ -107,10 +107,10 @@ __global__ void __launch_bounds__(256) k2_render_brute(const __grid_constant__ R
 					const int gy = trunc_cell(fdiv(-y, P.gw));     // :1003-1004 (hmap_c0.y == 0)
 					if (gx < 0 || gy < 0 || gx >= P.map_w || gy >= P.map_h) break;
 					const size_t cell = (size_t)gx + (size_t)gy * (size_t)P.map_w;
-					const double s = __ldg(P.surf + cell);
+					const double s = __ldg(P.surf + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h));
 					k += 1ULL;
 					if (z < s) {                                    // :1016
-						rgba = hit_colour(P, __ldg(P.color + cell));
+						rgba = hit_colour(P, __ldg(P.color + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h)));
 						real_hit = true;
 						first_hit = (k - 1ULL > 0x7FFFFFFFULL) ? 0x7FFFFFFF : (int)(k - 1ULL);
 						break;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(256) k2_render_brute(const __grid_constant__ R
 			}
 			if (!real_hit) rgba = miss_colour(P, ray.dz);
 			else tally.surf_hit = 1u;
-			P.fb[(size_t)py * (size_t)P.W + (size_t)px] = rgba;   // SetPixel, main/hmap.cpp:139-154
+			P.fb[HMRM_CHECKED(P, (size_t)py * (size_t)P.W + (size_t)px, (size_t)P.W * (size_t)P.H)] = rgba;   // SetPixel, main/hmap.cpp:139-154
 			if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
 		}
 		commit_tally<kStats>(P, active, tally);

@@ -164,7 +164,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 	auto probe = [&](int lvl, int vx, int vy) -> int {   // dilated block maximum, in the z units of the model
 		const uint2 d = P.lv_desc[lvl];
 		const unsigned idx = d.x + (unsigned)(vy >> (k + lvl)) * d.y + (unsigned)(vx >> (k + lvl));
-		return (int)__ldg(P.lv + idx);
+		return (int)__ldg(P.lv + HMRM_CHECKED(P, idx, P.lv_total));
 	};
 	// `above q` / `below q` with the model's error (< 1.6/16 Zq) and Zq16's rounding (ties at q +- 1/2) covered
 	auto above = [&](int vz, int q) -> bool { return vz > (q << 4) + HMRM_LIN_ZMARGIN && q < 65535; };
@@ -289,7 +289,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			}
 			const size_t cell = (size_t)gx + (size_t)gy * (size_t)P.map_w;
 			if (kStats) fetches += 1u;
-			if (az.p < __ldg(P.surf + cell)) {
+			if (az.p < __ldg(P.surf + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h))) {
 				hit_cell = (unsigned)cell;      // colour fetched by the caller, once the whole warp is out of the loop
 				real_hit = true;
 				first_hit = (n > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)n;
@@ -323,7 +323,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			const size_t cell = (size_t)gx + (size_t)gy * (size_t)P.map_w;
 			kk += 1ULL;
 			if (kStats) fetches += 1u;
-			if (az.p < __ldg(P.surf + cell)) {
+			if (az.p < __ldg(P.surf + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h))) {
 				hit_cell = (unsigned)cell;      // colour fetched by the caller, once the whole warp is out of the loop
 				real_hit = true;
 				first_hit = (kk - 1ULL > 0x7FFFFFFFULL) ? 0x7FFFFFFF : (int)(kk - 1ULL);
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin
 		const int ty_seq = (int)(tile / (unsigned)P.tiles_x);
 		const int tx = (int)(tile - (unsigned)ty_seq * (unsigned)P.tiles_x);
 		// longest-processing-time-first: a few grazing tiles take ~50x the mean, so they must start early
-		const int ty = P.row_order ? __ldg(P.row_order + ty_seq) : ty_seq;
+		const int ty = P.row_order ? __ldg(P.row_order + HMRM_CHECKED(P, ty_seq, P.tiles_y)) : ty_seq;
 		const int px = tx * 8 + (lane & 7);
 		const int py = P.row_begin + (P.tile_y_first + ty * P.tile_y_step) * 4 + (lane >> 3);
 		const bool active = pixel_selected(P, px, py);
@@ -392,11 +392,11 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin
 				}
 				if (!real_hit) rgba = miss_colour(P, ray.dz);
 				else {
-					rgba = hit_colour(P, __ldg(P.color + hit_cell));
+					rgba = hit_colour(P, __ldg(P.color + HMRM_CHECKED(P, hit_cell, (size_t)P.map_w * (size_t)P.map_h)));
 					tally.surf_hit = 1u;
 				}
 			}
-			P.fb[(size_t)py * (size_t)P.W + (size_t)px] = rgba;
+			P.fb[HMRM_CHECKED(P, (size_t)py * (size_t)P.W + (size_t)px, (size_t)P.W * (size_t)P.H)] = rgba;
 			if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
 		}
 		commit_tally<kStats>(P, active, tally);

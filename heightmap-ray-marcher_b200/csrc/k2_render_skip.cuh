@@ -159,7 +159,7 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 	auto probe = [&](int level, int vx, int vy) -> int {
 		const uint2 d = P.lv_desc[level];
 		const unsigned idx = d.x + (unsigned)(vy >> (k + level)) * d.y + (unsigned)(vx >> (k + level));
-		return (int)__ldg(P.lv + idx);
+		return (int)__ldg(P.lv + HMRM_CHECKED(P, idx, P.lv_total));
 	};
 	// extent (clipped to the grid) of the neighbourhood a level-`level` texel covers, in fixed-point units
 	auto extent = [&](int level, int v, unsigned grid, int &lo, int &hi) {
@@ -223,11 +223,11 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 			bool hit = cur.zq < q;
 			if (kStats) tally.dbg[5] += 1u;
 			if (!hit) {
-				hit = az.p < __ldg(P.surf + cell);     // Zq tie: decide in FP64
+				hit = az.p < __ldg(P.surf + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h));     // Zq tie: decide in FP64
 				if (kStats) fetches += 1u;
 			}
 			if (hit) {
-				rgba = hit_colour(P, __ldg(P.color + cell));
+				rgba = hit_colour(P, __ldg(P.color + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h)));
 				real_hit = true;
 				if (kStats) first_hit = (steps > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)steps;
 				steps += 1u;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256, 4) k2_render_skip(const __grid_constant__
 		const int ty_seq = (int)(tile / (unsigned)P.tiles_x);
 		const int tx = (int)(tile - (unsigned)ty_seq * (unsigned)P.tiles_x);
 		// longest-processing-time-first: a few grazing tiles take ~50x the mean, so they must start early
-		const int ty = P.row_order ? __ldg(P.row_order + ty_seq) : ty_seq;
+		const int ty = P.row_order ? __ldg(P.row_order + HMRM_CHECKED(P, ty_seq, P.tiles_y)) : ty_seq;
 		const int px = tx * 8 + (lane & 7);
 		const int py = P.row_begin + (P.tile_y_first + ty * P.tile_y_step) * 4 + (lane >> 3);
 		const bool active = pixel_selected(P, px, py);
@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(256, 4) k2_render_skip(const __grid_constant__
 				if (!real_hit) rgba = miss_colour(P, ray.dz);
 				else tally.surf_hit = 1u;
 			}
-			P.fb[(size_t)py * (size_t)P.W + (size_t)px] = rgba;
+			P.fb[HMRM_CHECKED(P, (size_t)py * (size_t)P.W + (size_t)px, (size_t)P.W * (size_t)P.H)] = rgba;
 			if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
 		}
 		commit_tally<kStats>(P, active, tally);

@@ -33,6 +33,7 @@ struct RenderParams {
 	// k2_render_lin: grid extents in fixed-point units (map << fx_bits, <= 2^30) and the same minus twice the margin;
 	// host-computed so that the march loop reads them as constant-bank operands
 	unsigned lin_grid_x, lin_grid_y, lin_span_x, lin_span_y;
+	unsigned long long lv_total;   // u16 elements behind `lv` (bounds checks of the -DHMRM_BOUNDS_CHECK test build)
 	// map
 	int map_w, map_h;
 	// image plane (host-built, frame_setup.h)
@@ -74,5 +75,13 @@ struct RenderParams {
 };
 
 } // namespace hmrm
+
+// Test build (-DHMRM_BOUNDS_CHECK, tools/bounds_check.sh): every table index of the traversal kernels is validated;
+// a bad one sets bit 3 of DeviceStats::status (the parity tests then fail on the status) and reads element 0 instead.
+#ifdef HMRM_BOUNDS_CHECK
+#define HMRM_CHECKED(P, idx, limit) (((unsigned long long)(idx) < (unsigned long long)(limit)) ? (idx) : (atomicOr(&(P).stats->status, 8u), (idx) * 0))
+#else
+#define HMRM_CHECKED(P, idx, limit) (idx)
+#endif
 
 #endif
