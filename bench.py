@@ -345,12 +345,33 @@ def ours_arm(args, wl) -> None:
     E2E_DEPTH = 3                               # frames that may stay in flight behind the newest one
     host_bufs = [h_out] + [binding.pinned_empty((H, W, 4)) for _ in range(E2E_DEPTH)]
 
+    # bands at N > 1: ONE host frame in POSIX shared memory, page-locked by every rank; each rank copies its own tile
+    # rows out over its own PCIe link (hmrm_render_async with band_count > 1), a barrier completes the frame
+    shared = None
+    if bands and world > 1:
+        from multiprocessing import shared_memory
+
+        name = [None]
+        if rank == 0:
+            shared = shared_memory.SharedMemory(create=True, size=H * W * 4)
+            name[0] = shared.name
+        dist.broadcast_object_list(name, src=0)
+        if rank != 0:
+            shared = shared_memory.SharedMemory(name=name[0])
+            from multiprocessing import resource_tracker
+
+            resource_tracker.unregister(shared._name, "shared_memory")     # rank 0 owns (and unlinks) the segment
+        shared_np = np.ndarray((H, W, 4), dtype=np.uint8, buffer=shared.buf)
+        if binding.load_library().hmrm_host_register(shared_np.ctypes.data, H * W * 4) != 0:
+            raise SystemExit("hmrm_host_register failed")
+        e2e_token = torch.zeros(1, device=f"cuda:{local}")
+
     def e2e_step(i: int, n: int) -> None:
         if bands and world > 1:
-            full = render_step(n)              # bands + NCCL gather; rank 0 then reads the frame back
-            if rank == 0:
-                h_out_t.copy_(full, non_blocking=True)
-            stream.synchronize()
+            r.render_async(frame_of(n), shared_np)
+            r.wait()
+            dist.all_reduce(e2e_token)         # the frame is complete in host memory once every rank's copy is
+            torch.cuda.synchronize()
         else:
             # the library's streaming call: the newest frames render while an older one is still being copied to the
             # host; after wait_pending(d) frame i-d is complete in its host buffer (d + 1 buffers rotate)
@@ -454,7 +475,9 @@ def ours_arm(args, wl) -> None:
                          "note": "algorithmic bytes = 8*S + 4*hits + 4*W*H with S = reference-equivalent steps"},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": W * H * 4,
-                    "api": "hmrm_render_async + hmrm_wait_pending(3): every frame lands in pinned host memory; the "
+                    "api": ("hmrm_render_async with band_count = N into ONE host frame in shared memory, page-locked by every "
+                            "rank: each rank copies its own tile rows out over its own PCIe link; all-reduce as the barrier")
+                    if (bands and world > 1) else "hmrm_render_async + hmrm_wait_pending(3): every frame lands in pinned host memory; the "
                            "copy-out of frame n overlaps the kernels of the next frames (four device + four host "
                            "buffers)"},
             "gpu_launches": launches,
@@ -479,6 +502,21 @@ def ours_arm(args, wl) -> None:
             line["cpu_baseline"] = cb
         emit(line)
 
+    if shared is not None:
+        ok_host = True
+        if rank == 0:
+            # the host frame of the last e2e step must be the frame itself
+            whole = frame_of(my_frames[-1])
+            whole.band_count = whole.band_index = 0
+            ok_host = bool(np.array_equal(shared_np, r.render(whole)))
+        binding.load_library().hmrm_host_unregister(shared_np.ctypes.data)
+        del shared_np
+        dist.barrier()
+        shared.close()
+        if rank == 0:
+            shared.unlink()
+            if not ok_host:
+                raise SystemExit("bands e2e: the shared host frame differs from the frame rendered whole")
     if peer is not None:
         peer.close()
     r.close()

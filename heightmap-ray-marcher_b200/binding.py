@@ -99,6 +99,8 @@ PROTOTYPES = {
                                C.POINTER(C.c_double)]),
     "hmrm_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
     "hmrm_host_free": (None, [C.c_void_p]),
+    "hmrm_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "hmrm_host_unregister": (C.c_int, [C.c_void_p]),
     "hmrm_device_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "hmrm_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hmrm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -906,8 +906,31 @@ int hmrm_render_async(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
 	if (rb == 0 && re == 0) re = f->screen_height;
 	const size_t row_bytes = (size_t)f->screen_width * 4;
 	HMRM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[slot], 0));
-	HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + (size_t)rb * row_bytes, (const uint8_t *)fb + (size_t)rb * row_bytes,
-	                             (size_t)(re - rb) * row_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+	if (f->band_count > 1) {
+		// interleaved bands: only the tile rows this launch rendered go to the host (several ranks may fill one
+		// shared, registered host frame, each over its own PCIe link); one strided copy + the ragged last tile row
+		const int tile_rows = (re - rb + 3) / 4;
+		const int owned = tile_rows > f->band_index ? (tile_rows - f->band_index + f->band_count - 1) / f->band_count : 0;
+		if (owned > 0) {
+			const int last_tile = f->band_index + (owned - 1) * f->band_count;
+			const int last_rows = (re - rb) - last_tile * 4 < 4 ? (re - rb) - last_tile * 4 : 4;
+			const int full = last_rows == 4 ? owned : owned - 1;
+			const size_t first = (size_t)(rb + f->band_index * 4) * row_bytes;
+			const size_t pitch = (size_t)f->band_count * 4 * row_bytes;
+			if (full > 0)
+				HMRM_CUDA(c, cudaMemcpy2DAsync(rgba_out + first, pitch, (const uint8_t *)fb + first, pitch, 4 * row_bytes,
+				                               (size_t)full, cudaMemcpyDeviceToHost, c->copy_stream));
+			if (full < owned) {
+				const size_t at = (size_t)(rb + last_tile * 4) * row_bytes;
+				HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + at, (const uint8_t *)fb + at, (size_t)last_rows * row_bytes,
+				                             cudaMemcpyDeviceToHost, c->copy_stream));
+			}
+		}
+	}
+	else {
+		HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + (size_t)rb * row_bytes, (const uint8_t *)fb + (size_t)rb * row_bytes,
+		                             (size_t)(re - rb) * row_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+	}
 	HMRM_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
 	c->copy_pending[slot] = true;
 	c->slot = slot;
@@ -1018,6 +1041,20 @@ int hmrm_host_alloc(void **ptr, size_t bytes) {
 
 void hmrm_host_free(void *ptr) {
 	if (ptr) cudaFreeHost(ptr);
+}
+
+int hmrm_host_register(void *ptr, size_t bytes) {
+	if (!ptr || bytes == 0) return HMRM_ERR_INVALID;
+	cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+	if (e != cudaSuccess) return fail(NULL, HMRM_ERR_CUDA, "cudaHostRegister(%zu) failed: %s", bytes, cudaGetErrorString(e));
+	return HMRM_OK;
+}
+
+int hmrm_host_unregister(void *ptr) {
+	if (!ptr) return HMRM_ERR_INVALID;
+	cudaError_t e = cudaHostUnregister(ptr);
+	if (e != cudaSuccess) return fail(NULL, HMRM_ERR_CUDA, "cudaHostUnregister failed: %s", cudaGetErrorString(e));
+	return HMRM_OK;
 }
 
 int hmrm_device_alloc(hmrm_ctx *c, size_t bytes, void **dptr) {

@@ -120,6 +120,8 @@ int hmrm_render(hmrm_ctx *ctx, const hmrm_frame *f, uint8_t *rgba_out);
 int hmrm_render_device(hmrm_ctx *ctx, const hmrm_frame *f, void *d_rgba_out, void *stream);
 /* persistent device framebuffer: render into it, copy rows [row_begin,row_end) to (pinned) host memory
  * asynchronously; hmrm_wait() joins.  Used for frame sharding (one frame in flight per context). */
+/* rgba_out always addresses the WHOLE frame; rows [row_begin, row_end) are written, and with band_count > 1 only
+ * the tile rows of this band (so several contexts / ranks can fill one host frame). */
 int hmrm_render_async(hmrm_ctx *ctx, const hmrm_frame *f, uint8_t *rgba_out);
 int hmrm_wait(hmrm_ctx *ctx);
 /* Streaming: up to four whole frames (cycle_period 1) may be in flight; the copy-out of one overlaps the kernels
@@ -149,6 +151,9 @@ int hmrm_get_ray(const hmrm_frame *f, double w, double h, double pos[3], double 
 /* pinned host memory helpers (so that callers without a CUDA binding can stage buffers) */
 int hmrm_host_alloc(void **ptr, size_t bytes);
 void hmrm_host_free(void *ptr);
+/* page-lock memory the caller owns (e.g. a POSIX shared-memory frame that several ranks fill with their bands) */
+int hmrm_host_register(void *ptr, size_t bytes);
+int hmrm_host_unregister(void *ptr);
 
 /* ---- peer frames: one big frame rendered by several GPUs of one node (one process per GPU) ----
  * The root rank allocates the frame on its device and exports a 64-byte handle (CUDA IPC); every other rank opens it

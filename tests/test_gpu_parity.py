@@ -363,3 +363,27 @@ def test_baseline_full_size_traversals_agree(hmrm, workload, frame_no):
             assert base[2] == other[2] and other[3] == 0
     finally:
         r.close()
+
+
+@pytest.mark.parametrize("world,height", [(2, 226), (3, 225), (8, 227), (5, 16)])
+def test_bands_fill_one_host_frame(hmrm, renderer, oracle, world, height):
+    """hmrm_render_async with band_count > 1 copies only this band's tile rows to the host (a strided copy plus the
+    ragged last tile row), so several ranks can fill ONE host frame, each over its own PCIe link."""
+    from heightmap_ray_marcher_b200 import binding
+
+    scene = dict(S.SCENE_BY_NAME["persp_graze"], height=height)
+    maps = H.load_scene_maps(scene, oracle)
+    H.configure(renderer, scene, maps)
+    full = renderer.render(H.product_frame(hmrm, renderer, scene)).copy()
+    host = binding.pinned_empty(full.shape)
+    host[:] = 0x5A
+    for r in range(world):
+        before = host.copy()
+        renderer.render_async(H.product_frame(hmrm, renderer, scene, band_count=world, band_index=r), host)
+        renderer.wait()
+        own = np.zeros(height, dtype=bool)
+        for t in range(r, (height + 3) // 4, world):
+            own[t * 4: min(t * 4 + 4, height)] = True
+        assert np.array_equal(host[own], full[own]), f"rank {r}: own rows"
+        assert np.array_equal(host[~own], before[~own]), f"rank {r}: rows of other ranks were touched"
+    assert np.array_equal(host, full)
