@@ -223,13 +223,31 @@ int main(int argc, char **argv) {
 		std::cerr << "hmap: no CUDA device; there is no CPU renderer\n";
 		return 1;
 	}
-	if (opt.gpus > available) {
-		std::cerr << "hmap: --gpus " << opt.gpus << " but only " << available << " device(s) present\n";
+	// HMAP_DEVICE_LIST=2,3,5 picks the CUDA devices --gpus counts over (a device may be listed more than once: several
+	// contexts then share it, which is how the multi-device paths are tested on a one-GPU box)
+	std::vector<int> device_ids;
+	if (const char *list = std::getenv("HMAP_DEVICE_LIST")) {
+		std::stringstream ls(list);
+		std::string item;
+		while (std::getline(ls, item, ',')) {
+			const int id = std::atoi(item.c_str());
+			if (id < 0 || id >= available) {
+				std::cerr << "hmap: HMAP_DEVICE_LIST names device " << id << " but " << available << " device(s) are present\n";
+				return 1;
+			}
+			device_ids.push_back(id);
+		}
+	}
+	else {
+		for (int i = 0; i < available; ++i) device_ids.push_back(i);
+	}
+	if (opt.gpus > (int)device_ids.size()) {
+		std::cerr << "hmap: --gpus " << opt.gpus << " but only " << device_ids.size() << " device(s) present\n";
 		return 1;
 	}
 	std::vector<Device> devs((size_t)opt.gpus);
 	for (int i = 0; i < opt.gpus; ++i) {
-		if (hmrm_create(i, &devs[(size_t)i].ctx) != HMRM_OK) die_hmrm(NULL, "hmrm_create");
+		if (hmrm_create(device_ids[(size_t)i], &devs[(size_t)i].ctx) != HMRM_OK) die_hmrm(NULL, "hmrm_create");
 	}
 	cfg.maps_changed = true;
 	push_maps(devs, cfg);
@@ -248,17 +266,20 @@ int main(int argc, char **argv) {
 	const std::clock_t t_start = std::clock();
 
 	if (opt.script_path.empty()) {
-		// ---- one frame; with several GPUs the frame is split into row bands (rows dealt in blocks of 4 tiles) ----
+		// ---- one frame; with several GPUs its 4-row tile rows are dealt round-robin to the devices (interleaved:
+		// sky rows cost nothing and terrain rows do, so contiguous bands balance badly) ----
 		hmrm_frame f = make_frame(cfg, opt);
 		const size_t bytes = (size_t)f.screen_width * (size_t)f.screen_height * 4;
 		ensure_host_frame(devs[0], bytes);
-		const int H = f.screen_height, G = opt.gpus;
+		const int G = opt.gpus;
 		for (int g = 0; g < G; ++g) {
 			hmrm_frame fb = f;
-			fb.row_begin = (int)((long long)H * g / G) & ~3;
-			fb.row_end = g + 1 == G ? H : ((int)((long long)H * (g + 1) / G) & ~3);
-			if (fb.row_begin >= fb.row_end) continue;
-			// every device writes its band straight into the one pinned host frame
+			if (G > 1) {
+				fb.band_count = G;
+				fb.band_index = g;
+				if (g * 4 >= f.screen_height) continue;       // more devices than tile rows
+			}
+			// every device copies its own tile rows straight into the one pinned host frame
 			if (hmrm_render_async(devs[(size_t)g].ctx, &fb, devs[0].host_frame) != HMRM_OK)
 				die_hmrm(devs[(size_t)g].ctx, "hmrm_render");
 			devs[(size_t)g].busy = true;
