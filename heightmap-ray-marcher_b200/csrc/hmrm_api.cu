@@ -561,6 +561,37 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	return HMRM_OK;
 }
 
+// D2H of what one launch rendered: rows [rb, re), or with band_count > 1 only the tile rows of that band (several
+// ranks may fill one shared, registered host frame, each over its own PCIe link): one strided copy + the ragged last
+// tile row.  Enqueued on the copy stream.
+int enqueue_copy_out(hmrm_ctx *c, const hmrm_frame *f, const uint32_t *fb, uint8_t *rgba_out, int rb, int re) {
+	const size_t row_bytes = (size_t)f->screen_width * 4;
+	if (f->band_count > 1) {
+		const int tile_rows = (re - rb + 3) / 4;
+		const int owned = tile_rows > f->band_index ? (tile_rows - f->band_index + f->band_count - 1) / f->band_count : 0;
+		if (owned > 0) {
+			const int last_tile = f->band_index + (owned - 1) * f->band_count;
+			const int last_rows = (re - rb) - last_tile * 4 < 4 ? (re - rb) - last_tile * 4 : 4;
+			const int full = last_rows == 4 ? owned : owned - 1;
+			const size_t first = (size_t)(rb + f->band_index * 4) * row_bytes;
+			const size_t pitch = (size_t)f->band_count * 4 * row_bytes;
+			if (full > 0)
+				HMRM_CUDA(c, cudaMemcpy2DAsync(rgba_out + first, pitch, (const uint8_t *)fb + first, pitch, 4 * row_bytes,
+				                               (size_t)full, cudaMemcpyDeviceToHost, c->copy_stream));
+			if (full < owned) {
+				const size_t at = (size_t)(rb + last_tile * 4) * row_bytes;
+				HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + at, (const uint8_t *)fb + at, (size_t)last_rows * row_bytes,
+				                             cudaMemcpyDeviceToHost, c->copy_stream));
+			}
+		}
+	}
+	else {
+		HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + (size_t)rb * row_bytes, (const uint8_t *)fb + (size_t)rb * row_bytes,
+		                             (size_t)(re - rb) * row_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+	}
+	return HMRM_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -899,38 +930,17 @@ int hmrm_render_async(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
 		}
 	}
 	if (c->copy_pending[slot]) HMRM_CUDA(c, cudaStreamWaitEvent(cs, c->ev_copied[slot], 0));
+	int rb = f->row_begin, re = f->row_end;
+	if (rb == 0 && re == 0) re = f->screen_height;
+	// (Rendering a frame that finds the pipeline idle as four interleaved bands, each copied out as soon as its kernel
+	// is done, was measured: four launches mean four tails, the stream turns kernel-bound and stays "idle", 0.59 ->
+	// 0.63 ms per frame.  Frames stay whole.)
 	rc = enqueue_render(c, f, fb, cs, true);
 	if (rc) return rc;
 	HMRM_CUDA(c, cudaEventRecord(c->ev_rendered[slot], cs));
-	int rb = f->row_begin, re = f->row_end;
-	if (rb == 0 && re == 0) re = f->screen_height;
-	const size_t row_bytes = (size_t)f->screen_width * 4;
 	HMRM_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_rendered[slot], 0));
-	if (f->band_count > 1) {
-		// interleaved bands: only the tile rows this launch rendered go to the host (several ranks may fill one
-		// shared, registered host frame, each over its own PCIe link); one strided copy + the ragged last tile row
-		const int tile_rows = (re - rb + 3) / 4;
-		const int owned = tile_rows > f->band_index ? (tile_rows - f->band_index + f->band_count - 1) / f->band_count : 0;
-		if (owned > 0) {
-			const int last_tile = f->band_index + (owned - 1) * f->band_count;
-			const int last_rows = (re - rb) - last_tile * 4 < 4 ? (re - rb) - last_tile * 4 : 4;
-			const int full = last_rows == 4 ? owned : owned - 1;
-			const size_t first = (size_t)(rb + f->band_index * 4) * row_bytes;
-			const size_t pitch = (size_t)f->band_count * 4 * row_bytes;
-			if (full > 0)
-				HMRM_CUDA(c, cudaMemcpy2DAsync(rgba_out + first, pitch, (const uint8_t *)fb + first, pitch, 4 * row_bytes,
-				                               (size_t)full, cudaMemcpyDeviceToHost, c->copy_stream));
-			if (full < owned) {
-				const size_t at = (size_t)(rb + last_tile * 4) * row_bytes;
-				HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + at, (const uint8_t *)fb + at, (size_t)last_rows * row_bytes,
-				                             cudaMemcpyDeviceToHost, c->copy_stream));
-			}
-		}
-	}
-	else {
-		HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + (size_t)rb * row_bytes, (const uint8_t *)fb + (size_t)rb * row_bytes,
-		                             (size_t)(re - rb) * row_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
-	}
+	rc = enqueue_copy_out(c, f, fb, rgba_out, rb, re);
+	if (rc) return rc;
 	HMRM_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
 	c->copy_pending[slot] = true;
 	c->slot = slot;
