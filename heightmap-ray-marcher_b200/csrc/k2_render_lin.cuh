@@ -184,7 +184,11 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		const unsigned j = n - base;
 		if (kStats) {                        // [6]: warp-level iterations (lane utilisation = lane iterations / 32 / this)
 			const unsigned am = __activemask();
-			if ((threadIdx.x & 31) == __ffs(am) - 1) tally.dbg[6] += 1u;
+			if ((threadIdx.x & 31) == __ffs(am) - 1) {
+				tally.dbg[6] += 1u;
+				// [8..11]: warp iterations with 1-8, 9-16, 17-24, 25-32 busy lanes
+				atomicAdd(&P.stats->dbg[8 + ((__popc(am) - 1) >> 3)], 1ULL);
+			}
 		}
 		// does this sample need the exact treatment?  (within the margin of the grid edge; at level 0 also of a cell edge)
 		bool exact = false;

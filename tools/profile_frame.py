@@ -45,6 +45,9 @@ for i in range(args.frames):
         print("   jumps %d (covering %d samples, %.1f/jump) plain-above %d descents %d cell-above %d cell-below %d slow-locate %d"
               % (d[0], d[1], d[1] / max(d[0], 1), d[2], d[3], d[4], d[5], d[7]))
         print("   lane iterations %d, warp iterations %d: %.1f of 32 lanes busy in the march loop" % (iters, d[6], iters / max(d[6], 1)))
+        if d[8] + d[9] + d[10] + d[11] == d[6] and d[6] > 0:
+            print("   warp iterations by busy lanes: 1-8: %.1f %%, 9-16: %.1f %%, 17-24: %.1f %%, 25-32: %.1f %%"
+                  % tuple(100.0 * d[8 + i] / d[6] for i in range(4)))
         print("   slowest tile %d clk (%.1f us at 1.965 GHz), mean tile %.0f clk, tiles > 100k clk: %d, most iterations of a ray: %d"
               % (d[8], d[8] / 1965.0, d[9] / max(st.rays / 32, 1), d[11], d[10]))
 r.close()
