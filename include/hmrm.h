@@ -134,8 +134,9 @@ int hmrm_get_stats(hmrm_ctx *ctx, hmrm_stats *out);            /* of the last re
  * by jumps, [2] single steps above a mip block, [3] level descents, [4] cell tests above the cell, [5] cell tests
  * below the quantised height (hits), [6] HMRM_TRAVERSAL_SKIP: warp-level loop iterations (lane utilisation of the
  * march loop = ([0]+[2]+[4]+[5]+[7]) / 32 / [6]); HMRM_TRAVERSAL_SKIP_FP64: refused jumps, [7] samples decided by the
- * exact FP64 expressions, [8]..[11] HMRM_TRAVERSAL_SKIP_FP64 only: slowest 8x4 tile in SM clocks, sum of tile clocks,
- * most loop iterations of any ray, tiles above 100 k clocks */
+ * exact FP64 expressions, [8]..[11] HMRM_TRAVERSAL_SKIP: warp-level iterations with 1-8 / 9-16 / 17-24 / 25-32 busy
+ * lanes; HMRM_TRAVERSAL_SKIP_FP64: slowest 8x4 tile in SM clocks, sum of tile clocks, most loop iterations of any ray,
+ * tiles above 100 k clocks */
 int hmrm_get_debug_counters(hmrm_ctx *ctx, int64_t out[12]);
 int hmrm_get_step_index(hmrm_ctx *ctx, int32_t *step_index);   /* int32 [H][W]: first-hit sample index,
                                                                   -1 box missed, -2 no surface hit */
