@@ -23,6 +23,10 @@ expect(171, "static void UpdateHeightmap()")
 expect(191, "}")
 expect(321, "&heightmap_width")
 expect(342, "&colormap_width")
+expect(612, "framebuf = new Uint8[")
+expect(698, "delete[] framebuf;")
+expect(699, "framebuf = new Uint8[")
+expect(1159, "delete[] framebuf;")
 expect(667, "up_vang")
 expect(672, ");")
 expect(952, "ImagePlane *ip;")
@@ -43,6 +47,9 @@ static void HmrmDie(const char *what) {
 	std::cerr << "hmrm: " << what << ": " << hmrm_last_error(g_hmrm) << "\n";
 	std::exit(1);
 }
+// framebuf is page-locked while it lives, so that the copy-out of a frame runs at PCIe speed (best effort)
+static void HmrmPin(Uint8 *buf) { hmrm_host_register(buf, (size_t)screen_width * (size_t)screen_height * 4); }
+static void HmrmUnpin(Uint8 *buf) { hmrm_host_unregister(buf); }
 '''
 
 UPDATE_BODY = r'''	// INTEGRATION.md §2: the prepass runs on the device (kernel K1) when the next frame needs it
@@ -103,9 +110,17 @@ for no, text in enumerate(lines, start=1):
         continue
     if no == 1129:
         continue
+    if no == 698:
+        out.append("\t\t\t\t\tHmrmUnpin(framebuf);")
+    if no == 1159:
+        out.append("\tHmrmUnpin(framebuf);")
     if no == 1161:
         out.append("\thmrm_destroy(g_hmrm);")
     out.append(text)
+    if no == 612:
+        out.append("\tHmrmPin(framebuf);")
+    if no == 699:
+        out.append("\t\t\t\t\tHmrmPin(framebuf);")
     if no in (321, 342):
         out.append("\t\t\t\tg_maps_dirty = true;")
     if no == 672:
