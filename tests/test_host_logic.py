@@ -32,3 +32,25 @@ def test_camera_basis_matches_oracle(hmrm, oracle):
         oracle.lib().oracle_camera_basis(hang, vang, ol, ou)
         assert [H.bits(v) for v in look] == [H.bits(v) for v in ol]
         assert [H.bits(v) for v in up] == [H.bits(v) for v in ou]
+
+
+def test_integration_patch_applies_to_the_reference_and_compiles(tmp_path):
+    """oracle/make_patched_reference.py (the INTEGRATION.md edits, addressed by line number and guarded by anchors)
+    still applies to the mounted reference, and the result compiles with the reference's own flags.  Running it needs
+    a GPU: tests/test_gpu_patched_reference.py."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    ref = Path("/root/reference/main/hmap.cpp")
+    if not ref.exists():
+        pytest.skip("/root/reference is not mounted")
+    out = tmp_path / "hmap_patched.cpp"
+    subprocess.run([sys.executable, str(root / "oracle" / "make_patched_reference.py"), str(ref), str(out)], check=True)
+    text = out.read_text()
+    assert text.count("hmrm_render(") == 1 and "#pragma omp parallel for" not in text and "delete ip;" not in text
+    res = subprocess.run(["g++", "-std=c++98", "-Wall", "-Wextra", "-Wconversion", "-fopenmp", "-fsyntax-only",
+                          "-I", str(root / "oracle" / "shim"), "-I", "/root/reference/src", "-I", "/root/reference/vendor",
+                          "-I", "/root/reference", "-I", str(root / "include"), str(out)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-2000:]
