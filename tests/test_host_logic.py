@@ -1,5 +1,7 @@
 """CPU: host-side mirror of the reference's type-level API (hmrm_deg2rad, hmrm_camera_basis, hmrm_get_ray —
 no device work) against known-answer vectors produced by the unmodified reference (tests/golden/kat.json)."""
+import pytest
+
 import helpers as H
 
 
