@@ -495,6 +495,8 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		P.lstride = e_stride ? std::atoi(e_stride) : 1;
 		if (P.lstride < 1) P.lstride = 1;
 		P.cell_exit_scale = e_exit ? (float)std::atof(e_exit) : 8.0f;
+		const char *e_climb = std::getenv("HMRM_CLIMB");
+		P.climb_ratio = e_climb ? (float)std::atof(e_climb) : 4.0f;
 		const int lstart = lmin + (e_start ? std::atoi(e_start) : 6) * P.lstride;
 		P.lstart = lstart > P.ltop ? P.ltop : (lstart < lmin ? lmin : lstart);
 		if (P.fx_bits < 1) traversal = HMRM_TRAVERSAL_BRUTE;

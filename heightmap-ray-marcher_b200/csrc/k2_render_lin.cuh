@@ -246,7 +246,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 					               __int2float_rz(room_y - (HMRM_LIN_MARGIN + 1)) * inv_ady);
 					est_z = lz.d < 0 ? __int2float_rz(vz - (q << 4) - (HMRM_LIN_ZMARGIN + 2)) * inv_adz : 3.0e38f;
 					// climb while z leaves room for (much) wider blocks and the wider neighbourhood is cleared too
-					if (!(est_z >= 4.0f * est_xy) || level + P.lstride > P.ltop) break;
+					if (!(est_z >= P.climb_ratio * est_xy) || level + P.lstride > P.ltop) break;
 					const int q2 = probe(level + P.lstride, vx, vy);
 					if (kStats) fetches += 1u;
 					if (!above(vz, q2)) break;
