@@ -31,7 +31,9 @@ extern "C" {
 
 /* arithmetic mode of the render kernel */
 #define HMRM_FP64_EXACT 0   /* bit-exact to the reference's RGBA8 framebuffer */
-#define HMRM_FP32_FAST  1   /* FP32 march, >= 99.5 % identical pixels */
+#define HMRM_FP32_FAST  1   /* FP32 front-end filter for rays that provably miss the box; the tolerance of the north
+                             * star is >= 99.5 % identical pixels, |step delta| <= 1 — by construction it changes none
+                             *  */
 
 /* traversal strategy (results are identical; this selects the kernel) */
 #define HMRM_TRAVERSAL_AUTO  0
@@ -118,10 +120,9 @@ void hmrm_frame_defaults(hmrm_frame *f);            /* the reference's defaults,
 int hmrm_render(hmrm_ctx *ctx, const hmrm_frame *f, uint8_t *rgba_out);
 /* device output (same layout) on `stream` (a cudaStream_t, NULL = ctx's own stream); asynchronous */
 int hmrm_render_device(hmrm_ctx *ctx, const hmrm_frame *f, void *d_rgba_out, void *stream);
-/* persistent device framebuffer: render into it, copy rows [row_begin,row_end) to (pinned) host memory
- * asynchronously; hmrm_wait() joins.  Used for frame sharding (one frame in flight per context). */
-/* rgba_out always addresses the WHOLE frame; rows [row_begin, row_end) are written, and with band_count > 1 only
- * the tile rows of this band (so several contexts / ranks can fill one host frame). */
+/* render into the context's device framebuffer(s) and copy rows [row_begin,row_end) to (pinned or registered) host
+ * memory asynchronously; hmrm_wait() joins.  rgba_out always addresses the WHOLE frame; with band_count > 1 only the
+ * tile rows of this band are written (so several contexts / ranks can fill one host frame). */
 int hmrm_render_async(hmrm_ctx *ctx, const hmrm_frame *f, uint8_t *rgba_out);
 int hmrm_wait(hmrm_ctx *ctx);
 /* Streaming: up to four whole frames (cycle_period 1) may be in flight; the copy-out of one overlaps the kernels
