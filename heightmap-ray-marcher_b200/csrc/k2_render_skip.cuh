@@ -78,9 +78,13 @@ __device__ __forceinline__ int steps_to_binade_edge(const AxisState &a) {
 	const double ap = fabs(a.p), aS = fabs(a.S);
 	const bool toward_zero = (a.S < 0.0) == (a.p > 0.0);
 	const double room = toward_zero ? fsub(ap, lo_edge) : fsub(fmul(lo_edge, 2.0), ap);
-	const double r = fdiv(room, aS);
-	if (!(r < (double)HMRM_JUMP_CAP)) return HMRM_JUMP_CAP;
-	const int n = __double2int_rz(r);
+	// an FP32 quotient is enough for an estimate (an IEEE double divide costs ~13 DADD issue slots); erring low only
+	// costs another round of the caller's loop
+	float inv;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(__double2float_rn(aS)));
+	const float r = __double2float_rz(room) * inv * 0.999f;
+	if (!(r < (float)HMRM_JUMP_CAP)) return HMRM_JUMP_CAP;
+	const int n = __float2int_rz(r);
 	return toward_zero ? n : n - 1;
 }
 
