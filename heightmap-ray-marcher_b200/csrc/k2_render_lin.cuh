@@ -283,7 +283,33 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			break;
 		}
 		else {
-			// undecided within the margin: reconstruct the exact sample and let the reference's own expressions decide
+			// Undecided in 16 bits.  If only the height is in doubt (cell known), look at the FP64 surface value itself
+			// before paying for an exact reconstruction: the model gives z_n within 1.6/16 Zq units, i.e. within
+			// delta = 0.125 / zq_scale world units (+ the rounding of mapping it back), and the reference's test is
+			// z_n < surf (main/hmap.cpp:1016).  This also settles the clamped q == 0 / q == 65535 cases.
+			if (!exact) {
+				const size_t cell = (size_t)(vx >> k) + (size_t)(vy >> k) * (size_t)P.map_w;
+				const double surf = __ldg(P.surf + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h));
+				if (kStats) fetches += 1u;
+				// Zr(z) = z * zq_scale + c, model value V = 16 Zr: z = (V / 16 - c) / zq_scale.  V / 16 - c is exact.
+				const double zc0 = P.zq_offset - HMRM_MAGIC;
+				const double z_est = fmul(fsub(fmul((double)vz, 0.0625), zc0), P.zq_inv);
+				const double delta = fadd(fmul(0.125, P.zq_inv), fmul(fabs(z_est), 8.9e-16));
+				if ((unsigned)(wz_hi + 32768) < 65536u && fadd(z_est, delta) < surf) {
+					if (kStats) tally.dbg[5] += 1u;
+					hit_cell = (unsigned)cell;
+					real_hit = true;
+					first_hit = (n > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)n;
+					n += 1u;
+					finished = true;
+					break;
+				}
+				if ((unsigned)(wz_hi + 32768) < 65536u && fsub(z_est, delta) > surf) {
+					if (kStats) tally.dbg[4] += 1u;
+					goto next_sample;          // certainly not below the surface: plain step, stay at the cell level
+				}
+			}
+			// still undecided: reconstruct the exact sample and let the reference's own expressions decide
 			if (kStats) tally.dbg[7] += 1u;
 			advance_exact(ax, ay, az, anchor, n);
 			const int gx = trunc_cell(fdiv(ax.p, P.gw)), gy = trunc_cell(fdiv(-ay.p, P.gw));
@@ -303,6 +329,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			}
 			level = 0;
 		}
+next_sample:
 		n += m;
 		{
 			const unsigned jn = n - base;
