@@ -480,7 +480,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		}
 		P.zq_scale = c->zq_scale;
 		P.zq_offset = c->zq_offset;
-		P.zq_inv = 1.0 / c->zq_scale;
+		P.inv_gw_up = (1.0 / f->grid_width) * 1.000001;
 		P.ltop = c->mip_levels - 1;
 		// lowest useful block: about one step wide (measured: profiles/r01_knob_sweep.txt)
 		const double step_cells = f->step_dist / f->grid_width;

@@ -283,30 +283,49 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			break;
 		}
 		else {
-			// Undecided in 16 bits.  If only the height is in doubt (cell known), look at the FP64 surface value itself
-			// before paying for an exact reconstruction: the model gives z_n within 1.6/16 Zq units, i.e. within
-			// delta = 0.125 / zq_scale world units (+ the rounding of mapping it back), and the reference's test is
-			// z_n < surf (main/hmap.cpp:1016).  This also settles the clamped q == 0 / q == 65535 cases.
-			if (!exact) {
-				const size_t cell = (size_t)(vx >> k) + (size_t)(vy >> k) * (size_t)P.map_w;
-				const double surf = __ldg(P.surf + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h));
-				if (kStats) fetches += 1u;
-				// Zr(z) = z * zq_scale + c, model value V = 16 Zr: z = (V / 16 - c) / zq_scale.  V / 16 - c is exact.
-				const double zc0 = P.zq_offset - HMRM_MAGIC;
-				const double z_est = fmul(fsub(fmul((double)vz, 0.0625), zc0), P.zq_inv);
-				const double delta = fadd(fmul(0.125, P.zq_inv), fmul(fabs(z_est), 8.9e-16));
-				if ((unsigned)(wz_hi + 32768) < 65536u && fadd(z_est, delta) < surf) {
-					if (kStats) tally.dbg[5] += 1u;
-					hit_cell = (unsigned)cell;
-					real_hit = true;
-					first_hit = (n > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)n;
-					n += 1u;
-					finished = true;
-					break;
-				}
-				if ((unsigned)(wz_hi + 32768) < 65536u && fsub(z_est, delta) > surf) {
-					if (kStats) tally.dbg[4] += 1u;
-					goto next_sample;          // certainly not below the surface: plain step, stay at the cell level
+			// Undecided in the integer model.  Before paying for an exact reconstruction, take an FP64 look: the reference's
+			// sample is P_n = P_a + (n - a) s up to the roundings of its n - a adds, each at most 2^-53 relative and the
+			// motion is monotone, so per axis |P_n - fma(n - a, s, P_a)| <= (n - a + 1) * 2^-53 * max(|P_a|, |P_n|).
+			// With that bound (doubled below) the reference's own expressions — (int)(x / gw), (int)(-y / gw),
+			// z < surf (main/hmap.cpp:1001-1016) — are decided unless the sample is within ~1e-12 of a cell edge or of the
+			// surface.  This settles the (-1, 0) truncation strip, cell and grid edges, clamped 16-bit heights and ties.
+			{
+				const double mj = (double)(n - anchor);
+				const double rel = fmul(fadd(mj, 2.0), 2.3e-16);
+				const double xe = __fma_rn(mj, ax.s, ax.p), ye = __fma_rn(mj, ay.s, ay.p), ze = __fma_rn(mj, az.s, az.p);
+				const double bx = fmul(rel, fmax(fabs(ax.p), fabs(xe))), by = fmul(rel, fmax(fabs(ay.p), fabs(ye)));
+				const double bz = fmul(rel, fmax(fabs(az.p), fabs(ze)));
+				const double qx = fdiv(xe, P.gw), qy = fdiv(-ye, P.gw);
+				// fl(x_true / gw) differs from qx by at most bx / gw + 2^-52 |q|; (int) truncates toward zero, so the only
+				// break points are the non-zero integers
+				const double axq = fabs(qx), ayq = fabs(qy);
+				const double ex_ = fadd(fmul(bx, P.inv_gw_up), fmul(axq, 4.5e-16)), ey_ = fadd(fmul(by, P.inv_gw_up), fmul(ayq, 4.5e-16));
+				const double fxq = fsub(axq, floor(axq)), fyq = fsub(ayq, floor(ayq));
+				const double near_x = axq < 1.0 ? fsub(1.0, axq) : fmin(fxq, fsub(1.0, fxq));
+				const double near_y = ayq < 1.0 ? fsub(1.0, ayq) : fmin(fyq, fsub(1.0, fyq));
+				if (axq < 2.0e9 && ayq < 2.0e9 && near_x > ex_ && near_y > ey_) {
+					const int gx = trunc_cell(qx), gy = trunc_cell(qy);
+					if (gx < 0 || gy < 0 || gx >= P.map_w || gy >= P.map_h) {
+						finished = true;                    // the reference's bounds test (:1006-1011): a miss
+						break;
+					}
+					const size_t cell = (size_t)gx + (size_t)gy * (size_t)P.map_w;
+					const double surf = __ldg(P.surf + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h));
+					if (kStats) fetches += 1u;
+					if (fadd(ze, bz) < surf) {
+						if (kStats) tally.dbg[5] += 1u;
+						hit_cell = (unsigned)cell;
+						real_hit = true;
+						first_hit = (n > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)n;
+						n += 1u;
+						finished = true;
+						break;
+					}
+					if (fsub(ze, bz) > surf) {
+						if (kStats) tally.dbg[4] += 1u;
+						level = 0;
+						goto next_sample;                   // certainly not below the surface: plain step, cell level next
+					}
 				}
 			}
 			// still undecided: reconstruct the exact sample and let the reference's own expressions decide

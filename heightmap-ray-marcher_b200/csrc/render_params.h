@@ -33,7 +33,7 @@ struct RenderParams {
 	// k2_render_lin: grid extents in fixed-point units (map << fx_bits, <= 2^30) and the same minus twice the margin;
 	// host-computed so that the march loop reads them as constant-bank operands
 	unsigned lin_grid_x, lin_grid_y, lin_span_x, lin_span_y;
-	double zq_inv;                 // 1 / zq_scale (host): maps the height model back to world units for the FP64 second look
+	double inv_gw_up;              // slightly more than 1 / grid_width (host): turns a position bound into a cell-coordinate bound
 	float climb_ratio;             // climb a level while the height leaves room for this many times the lateral room
 	unsigned long long lv_total;   // u16 elements behind `lv` (bounds checks of the -DHMRM_BOUNDS_CHECK test build)
 	// map
