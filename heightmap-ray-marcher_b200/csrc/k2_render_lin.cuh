@@ -25,10 +25,12 @@
 //                                          per axis and <= (Z_j - 16 q - 10) - 2 in height: the model itself is
 //                                          integer-exact (V_{j+m} - V_j is within 1 unit of m D / 2^16, V is monotone
 //                                          in j), so the end point needs no test.
-//     Any sample that is NOT decided with that margin is handed to advance_exact(): the exact FP64 position P_n is
-//     reconstructed from the last exact anchor with the binade-aware closed form (fact 1) and the reference's own
-//     expressions (divide, truncate, compare with the FP64 surface) decide it.  On the bench frame that happens
-//     for 2.6 % of the rays, once (mostly entry samples sitting on the grid edge).
+//     A sample that is NOT decided with that margin first gets an FP64 linear look (P_n = P_a + (n - a) s up to the
+//     accumulated rounding of the reference's adds, a bound of ~(n - a) 2^-53 relative): the reference's own divide /
+//     truncate / compare on that estimate decide unless the sample is within ~1e-12 of a cell edge or of the surface.
+//     Only then advance_exact() reconstructs the exact FP64 position P_n from the last exact anchor with the
+//     binade-aware closed form (fact 1).  On the bench frames that happens 0 times; the model's periodic re-anchoring
+//     is its only regular caller.
 //
 // Rays whose per-step motion or start position does not fit the integer model (steps of thousands of cells, a
 // start 2^31 units away, NaNs, no lateral motion at all) take the plain per-step loop of the brute kernel.
