@@ -175,6 +175,13 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 	for (;;) {
 		// keep the error bound: re-anchor the model on an exact position every HMRM_LIN_PERIOD samples
 		if (n - base >= HMRM_LIN_PERIOD) {
+			// (every 65536 samples at most: the place to notice a ray that will never end, ~2^31 samples: give up like a
+			// hang would, but flagged)
+			if (n >= 0x7FF00000u) {
+				tally.cut_off = 1u;
+				finished = true;
+				break;
+			}
 			advance_exact(ax, ay, az, anchor, n);
 			base = n;
 			if (!rebase()) {                 // left the representable range: finish with the per-step loop below
@@ -355,11 +362,6 @@ next_sample:
 		{
 			const unsigned jn = n - base;
 			wx = lin_acc(lx, jn); wy = lin_acc(ly, jn); wz = lin_acc(lz, jn);
-		}
-		if (n >= 0x7FF00000u) {          // ~2^31 samples: give up like a hang would, but flagged
-			tally.cut_off = 1u;
-			finished = true;
-			break;
 		}
 	}
 	}   // if (model)
