@@ -14,8 +14,14 @@ from __future__ import annotations
 from .binding import (  # noqa: F401
     FP32_FAST,
     FP64_EXACT,
+    FLAG_RAY_DUMP,
     FLAG_STATS,
     FLAG_STEP_INDEX,
+    LAYOUT_ROWMAJOR,
+    LAYOUT_TILE4,
+    LAYOUT_ZORDER,
+    PIXEL_RGB8,
+    PIXEL_RGBA8,
     ORTHOGRAPHIC,
     PERSPECTIVE,
     SPHERICAL,
@@ -37,5 +43,6 @@ from .binding import (  # noqa: F401
 __all__ = [
     "Renderer", "Frame", "Stats", "HmrmError", "load_library", "library_path", "deg2rad", "camera_basis",
     "get_ray", "PERSPECTIVE", "SPHERICAL", "ORTHOGRAPHIC", "FP64_EXACT", "FP32_FAST", "TRAVERSAL_AUTO",
-    "TRAVERSAL_BRUTE", "TRAVERSAL_SKIP", "FLAG_STATS", "FLAG_STEP_INDEX",
+    "TRAVERSAL_BRUTE", "TRAVERSAL_SKIP", "FLAG_STATS", "FLAG_STEP_INDEX", "FLAG_RAY_DUMP", "PIXEL_RGBA8", "PIXEL_RGB8",
+    "LAYOUT_ROWMAJOR", "LAYOUT_TILE4", "LAYOUT_ZORDER",
 ]

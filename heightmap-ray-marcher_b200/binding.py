@@ -18,7 +18,9 @@ PKG = Path(__file__).resolve().parent
 PERSPECTIVE, SPHERICAL, ORTHOGRAPHIC = 1, 2, 3          # main/hmap.cpp:104-106
 FP64_EXACT, FP32_FAST = 0, 1
 TRAVERSAL_AUTO, TRAVERSAL_BRUTE, TRAVERSAL_SKIP, TRAVERSAL_SKIP_FP64 = 0, 1, 2, 3
-FLAG_STATS, FLAG_STEP_INDEX = 1, 2
+FLAG_STATS, FLAG_STEP_INDEX, FLAG_RAY_DUMP = 1, 2, 4
+PIXEL_RGBA8, PIXEL_RGB8 = 0, 1
+LAYOUT_ROWMAJOR, LAYOUT_TILE4, LAYOUT_ZORDER = 0, 1, 2
 
 
 class HmrmError(RuntimeError):
@@ -43,7 +45,7 @@ class Frame(C.Structure):
         ("grid_width", C.c_double),
         ("step_dist", C.c_double),
         ("bg", C.c_uint8 * 3),
-        ("reserved0", C.c_uint8),
+        ("pixel_format", C.c_uint8),
         ("cycle", C.c_int32),
         ("cycle_period", C.c_int32),
         ("row_begin", C.c_int32),
@@ -82,6 +84,8 @@ PROTOTYPES = {
     "hmrm_set_maps_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
     "hmrm_synth_maps": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
     "hmrm_get_maps": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "hmrm_set_layout": (C.c_int, [C.c_void_p, C.c_int]),
+    "hmrm_get_layout": (C.c_int, [C.c_void_p]),
     "hmrm_update_heightmap": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.c_double, C.c_double]),
     "hmrm_get_heights": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hmrm_frame_defaults": (None, [C.POINTER(Frame)]),
@@ -92,12 +96,14 @@ PROTOTYPES = {
     "hmrm_wait_pending": (C.c_int, [C.c_void_p, C.c_int]),
     "hmrm_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "hmrm_get_step_index": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hmrm_get_ray_dump": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hmrm_get_debug_counters": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "hmrm_deg2rad": (C.c_double, [C.c_double]),
     "hmrm_camera_basis": (None, [C.c_double, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "hmrm_get_ray": (C.c_int, [C.POINTER(Frame), C.c_double, C.c_double, C.POINTER(C.c_double),
                                C.POINTER(C.c_double)]),
     "hmrm_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t]),
+    "hmrm_host_alloc_flags": (C.c_int, [C.POINTER(C.c_void_p), C.c_size_t, C.c_uint32]),
     "hmrm_host_free": (None, [C.c_void_p]),
     "hmrm_host_register": (C.c_int, [C.c_void_p, C.c_size_t]),
     "hmrm_host_unregister": (C.c_int, [C.c_void_p]),
@@ -106,6 +112,11 @@ PROTOTYPES = {
     "hmrm_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "hmrm_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "hmrm_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "hmrm_render_peer": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "hmrm_peer_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]),
+    "hmrm_peer_release": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "hmrm_peer_status": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "hmrm_debug_aabb": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -255,6 +266,15 @@ class Renderer:
         lum = (C.c_double * 3)(self.lum_r, self.lum_g, self.lum_b)
         self._check(self._lib.hmrm_update_heightmap(self._h, lum, self.min_height, self.max_height))
 
+    def set_layout(self, layout: int) -> None:
+        """Layout of the height pyramid (LAYOUT_*); rebuilds the pyramid."""
+        self._check(self._lib.hmrm_set_layout(self._h, int(layout)))
+        if self.map_width:
+            self.update_heightmap()
+
+    def get_layout(self) -> int:
+        return int(self._lib.hmrm_get_layout(self._h))
+
     def heights(self) -> np.ndarray:
         out = np.empty((self.map_height, self.map_width), dtype=np.float64)
         self._check(self._lib.hmrm_get_heights(self._h, out.ctypes.data))
@@ -282,9 +302,10 @@ class Renderer:
     def render(self, frame: Frame | None = None, out: np.ndarray | None = None, **overrides) -> np.ndarray:
         """One frame (main/hmap.cpp:952-1058) into a host RGBA8 [H,W,4] array."""
         f = frame if frame is not None else self.frame(**overrides)
+        channels = 3 if f.pixel_format == PIXEL_RGB8 else 4
         if out is None:
-            out = np.zeros((f.screen_height, f.screen_width, 4), dtype=np.uint8)
-        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == f.screen_height * f.screen_width * 4
+            out = np.zeros((f.screen_height, f.screen_width, channels), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.flags.c_contiguous and out.size == f.screen_height * f.screen_width * channels
         self._check(self._lib.hmrm_render(self._h, C.byref(f), out.ctypes.data))
         return out
 
@@ -334,18 +355,47 @@ class Renderer:
     def ipc_close(self, dptr: int) -> None:
         self._check(self._lib.hmrm_ipc_close(self._h, C.c_void_p(dptr)))
 
+    def ray_dump(self, frame: Frame) -> np.ndarray:
+        """[H, W, 10] float64 of the last FLAG_RAY_DUMP render: pos, dir, distance(), entry point — as the DEVICE computed them."""
+        out = np.empty((frame.screen_height, frame.screen_width, 10), dtype=np.float64)
+        self._check(self._lib.hmrm_get_ray_dump(self._h, out.ctypes.data))
+        return out
+
+    def render_peer(self, frame: Frame, d_frame: int, d_ctrl: int, use: int, stream=None) -> None:
+        self._check(self._lib.hmrm_render_peer(self._h, C.byref(frame), C.c_void_p(d_frame), C.c_void_p(d_ctrl), use,
+                                               _ptr(stream)))
+
+    def peer_wait(self, d_ctrl: int, use: int, ranks: int, stream=None) -> None:
+        self._check(self._lib.hmrm_peer_wait(self._h, C.c_void_p(d_ctrl), use, ranks, _ptr(stream)))
+
+    def peer_release(self, d_ctrl: int, use: int, stream=None) -> None:
+        self._check(self._lib.hmrm_peer_release(self._h, C.c_void_p(d_ctrl), use, _ptr(stream)))
+
+    def peer_status(self, d_ctrl: int):
+        out = (C.c_uint32 * 3)()
+        self._check(self._lib.hmrm_peer_status(self._h, C.c_void_p(d_ctrl), out))
+        return tuple(out)
+
+    def debug_aabb(self, rays: np.ndarray, boxes: np.ndarray) -> np.ndarray:
+        """The device's slab test on [n,6] rays (pos, dir) and [n,6] boxes (c0, c1) -> [n,5] (distance, hit, entry)."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64)
+        boxes = np.ascontiguousarray(boxes, dtype=np.float64)
+        out = np.empty((rays.shape[0], 5), dtype=np.float64)
+        self._check(self._lib.hmrm_debug_aabb(self._h, rays.shape[0], rays.ctypes.data, boxes.ctypes.data, out.ctypes.data))
+        return out
+
     def step_index(self, frame: Frame) -> np.ndarray:
         out = np.empty((frame.screen_height, frame.screen_width), dtype=np.int32)
         self._check(self._lib.hmrm_get_step_index(self._h, out.ctypes.data))
         return out
 
 
-def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+def pinned_empty(shape, dtype=np.uint8, write_combined: bool = False) -> np.ndarray:
     """numpy array over page-locked host memory (hmrm_host_alloc); freed when garbage collected."""
     lib = load_library()
     nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
     p = C.c_void_p()
-    rc = lib.hmrm_host_alloc(C.byref(p), nbytes)
+    rc = lib.hmrm_host_alloc_flags(C.byref(p), nbytes, 1 if write_combined else 0)
     if rc:
         raise HmrmError(rc, lib.hmrm_last_error(None).decode())
     buf = (C.c_uint8 * nbytes).from_address(p.value)

@@ -23,6 +23,7 @@
 #include "k2_render_brute.cuh"
 #include "k2_render_skip.cuh"
 #include "k2_render_lin.cuh"
+#include "peer_sync.cuh"
 #include "render_params.h"
 #include "synth_fbm.h"
 
@@ -50,12 +51,28 @@ struct LaunchSlot {
 	double row_key[8];
 	bool row_key_valid;
 	int row_sky_first;           // schedule position of the first tile row that only looks above the horizon
+	int32_t *d_step_index;       // HMRM_FLAG_STEP_INDEX output of the launch that used this slot
+	size_t step_cap;             // pixels
+	double *d_ray_dump;          // HMRM_FLAG_RAY_DUMP output, [pixels][10]
+	size_t dump_cap;             // pixels
 };
 
 } // namespace
 
+// Experiment knobs (environment, read ONCE in hmrm_create): they never change a result, only how the work is
+// scheduled / how many fetches are issued.
+struct Knobs {
+	bool no_row_order, no_batch, debug_sched;
+	int lmin_bias, lstride, lstart;
+	float cell_exit, climb;
+	bool zq_shrink_set;
+	double zq_shrink;
+	unsigned long long peer_timeout_ns;
+};
+
 struct hmrm_ctx {
 	int device;
+	Knobs knobs;
 	int num_sms;
 	cudaStream_t stream;          // compute stream of frame-buffer slot 0 (and of everything that is not a frame)
 	cudaStream_t ring_stream[kFrameRing];   // compute stream of each frame buffer ([0] == stream): frame n+1 starts
@@ -74,9 +91,13 @@ struct hmrm_ctx {
 	uint16_t *d_mip;             // what the traversal reads, levels 0..mip_levels-1 back to back: level 0 = Zq(surf)
 	                             // per cell, level l >= 1 = 3x3-block dilation of the plain max-mip level l
 	uint16_t *d_dil;             // scratch: the plain (undilated) max-mip levels 1.., input of the dilation
-	size_t mip_offset[16];
+	size_t mip_offset[16];       // element offset of level l inside d_mip (sizes depend on the layout)
+	size_t plain_offset[16];     // element offset of plain level l (>= 1) inside d_dil (row-major)
 	int mip_w[16], mip_h[16];
 	int mip_levels;
+	int layout;                  // HMRM_LAYOUT_* of d_mip (pyramid_layout.cuh); fixed while maps are allocated
+	int layout_wanted;           // takes effect at the next hmrm_update_heightmap
+	unsigned int *d_k1_counter;  // k1_mip_upper's arrival counter
 	double zq_scale, zq_offset;
 	bool skip_ready;
 
@@ -93,14 +114,13 @@ struct hmrm_ctx {
 	cudaStream_t copy_stream;
 	cudaEvent_t ev_rendered[kFrameRing], ev_copied[kFrameRing];
 	bool copy_pending[kFrameRing];
+	int fb_format;               // pixel format of what the ring holds (a change re-zeroes it, like a new resolution)
 	int slot;                    // buffer of the most recent hmrm_render_async
-	int32_t *d_step_index;
-	size_t step_index_cap;
 
 	// per-launch resources, used round-robin so that up to kLaunchSlots kernels of this context may be in flight
 	LaunchSlot slots[kLaunchSlots];
 	int launch_next, launch_last;
-	bool last_had_stats, last_had_step_index, timing_valid;
+	bool last_had_stats, last_had_step_index, last_had_ray_dump, timing_valid;
 	int last_w, last_h;
 	cudaStream_t last_stream;    // stream of the most recent render (the caller's, for hmrm_render_device)
 };
@@ -142,6 +162,22 @@ __global__ void __launch_bounds__(256) k_synth_maps(uint32_t log2n, uint32_t see
 	}
 }
 
+// the device's slab test on caller-supplied rays and boxes (hmrm_debug_aabb): the very function the render kernels call
+__global__ void k_debug_aabb(int n, const double *rays, const double *boxes, double *out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	Ray r;
+	r.ox = rays[6 * i + 0]; r.oy = rays[6 * i + 1]; r.oz = rays[6 * i + 2];
+	r.dx = rays[6 * i + 3]; r.dy = rays[6 * i + 4]; r.dz = rays[6 * i + 5];
+	double ex = 0.0, ey = 0.0, ez = 0.0, dist = 0.0;
+	const bool hit = box_entry_at(boxes + 6 * i, boxes + 6 * i + 3, r, ex, ey, ez, dist);
+	out[5 * i + 0] = dist;
+	out[5 * i + 1] = hit ? 1.0 : 0.0;
+	out[5 * i + 2] = hit ? ex : 0.0;
+	out[5 * i + 3] = hit ? ey : 0.0;
+	out[5 * i + 4] = hit ? ez : 0.0;
+}
+
 int drain(hmrm_ctx *c) {
 	for (int i = 0; i < kFrameRing; ++i) HMRM_CUDA(c, cudaStreamSynchronize(c->ring_stream[i]));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->copy_stream));
@@ -166,6 +202,16 @@ void free_maps(hmrm_ctx *c) {
 	c->maps_set = c->heights_set = false;
 }
 
+// element offsets of the pyramid levels for `layout` (mip_w / mip_h / mip_levels are set); returns the total
+size_t layout_pyramid(hmrm_ctx *c, int layout) {
+	size_t total = 0;
+	for (int l = 0; l < c->mip_levels; ++l) {
+		c->mip_offset[l] = total;
+		total += (pyr_level_elems(layout, c->mip_w[l], c->mip_h[l]) + 63) & ~(size_t)63;
+	}
+	return total;
+}
+
 int alloc_maps(hmrm_ctx *c, int32_t w, int32_t h) {
 	if (w < 1 || h < 1 || w > 32768 || h > 32768)
 		return fail(c, HMRM_ERR_INVALID, "map size %dx%d outside [1,32768]", w, h);
@@ -181,21 +227,26 @@ int alloc_maps(hmrm_ctx *c, int32_t w, int32_t h) {
 	HMRM_CUDA(c, cudaMalloc(&c->d_color, n * 4));
 	HMRM_CUDA(c, cudaMalloc(&c->d_surf, n * 8));
 	// mip pyramid of 16-bit conservative heights: level l is ceil(w/2^l) x ceil(h/2^l), up to a single texel
-	size_t total = 0;
 	int lw = w, lh = h, levels = 0;
+	size_t plain_total = 0;
 	for (;;) {
 		c->mip_w[levels] = lw;
 		c->mip_h[levels] = lh;
-		c->mip_offset[levels] = total;
-		total += ((size_t)lw * (size_t)lh + 63) & ~(size_t)63;
+		c->plain_offset[levels] = plain_total;
+		if (levels >= 1) plain_total += ((size_t)lw * (size_t)lh + 63) & ~(size_t)63;
 		levels += 1;
 		if ((lw == 1 && lh == 1) || levels == 16) break;
 		lw = (lw + 1) / 2;
 		lh = (lh + 1) / 2;
 	}
 	c->mip_levels = levels;
-	HMRM_CUDA(c, cudaMalloc(&c->d_mip, total * 2));
-	if (levels > 1) HMRM_CUDA(c, cudaMalloc(&c->d_dil, (total - c->mip_offset[1]) * 2));
+	// the pyramid buffer fits whichever layout is selected later (hmrm_set_layout + hmrm_update_heightmap)
+	size_t cap = 0;
+	for (int layout = 0; layout < 3; ++layout) cap = std::max(cap, layout_pyramid(c, layout));
+	c->layout = c->layout_wanted;
+	layout_pyramid(c, c->layout);
+	HMRM_CUDA(c, cudaMalloc(&c->d_mip, cap * 2));
+	if (levels > 1) HMRM_CUDA(c, cudaMalloc(&c->d_dil, plain_total * 2));
 	c->map_w = w;
 	c->map_h = h;
 	return HMRM_OK;
@@ -218,8 +269,8 @@ int ensure_tables(hmrm_ctx *c, int W, int H) {
 	return HMRM_OK;
 }
 
-int ensure_framebuffer(hmrm_ctx *c, int W, int H) {
-	if (c->d_fb[0] && c->fb_w == W && c->fb_h == H) return HMRM_OK;
+int ensure_framebuffer(hmrm_ctx *c, int W, int H, int format) {
+	if (c->d_fb[0] && c->fb_w == W && c->fb_h == H && c->fb_format == format) return HMRM_OK;
 	if (int rc = drain(c)) return rc;
 	for (int i = 0; i < kFrameRing; ++i) {
 		c->copy_pending[i] = false;
@@ -235,6 +286,7 @@ int ensure_framebuffer(hmrm_ctx *c, int W, int H) {
 	c->slot = 0;
 	c->fb_w = W;
 	c->fb_h = H;
+	c->fb_format = format;
 	return HMRM_OK;
 }
 
@@ -260,6 +312,8 @@ int validate_frame(hmrm_ctx *c, const hmrm_frame *f, int *row_begin, int *row_en
 		return fail(c, HMRM_ERR_INVALID, "need cycle_period >= 1 and 0 <= cycle < cycle_period");
 	if (f->precision != HMRM_FP64_EXACT && f->precision != HMRM_FP32_FAST)
 		return fail(c, HMRM_ERR_INVALID, "unknown precision %d", f->precision);
+	if (f->pixel_format != HMRM_PIXEL_RGBA8 && f->pixel_format != HMRM_PIXEL_RGB8)
+		return fail(c, HMRM_ERR_INVALID, "unknown pixel_format %d", (int)f->pixel_format);
 	int rb = f->row_begin, re = f->row_end;
 	if (rb == 0 && re == 0) re = f->screen_height;
 	if (rb < 0 || re > f->screen_height || rb >= re)
@@ -360,7 +414,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	// camera position or heading, so a flythrough computes it once.
 	P.row_order = NULL;
 	P.batch_from_tile = 0xFFFFFFFFu;
-	if (f->projection != HMRM_ORTHOGRAPHIC && P.tiles_y > 1 && !std::getenv("HMRM_NO_ROW_ORDER")) {
+	if (f->projection != HMRM_ORTHOGRAPHIC && P.tiles_y > 1 && !c->knobs.no_row_order) {
 		const double key[8] = {(double)f->projection, (double)W, (double)H, f->vang, f->hfov, (double)row_begin,
 		                       (double)(P.tile_y_first * 65536 + P.tile_y_step), (double)P.tiles_y};
 		if (!slot.row_key_valid || std::memcmp(key, slot.row_key, sizeof key) != 0) {
@@ -403,39 +457,18 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		}
 		P.row_order = slot.d_row_order;
 		// (only when the camera is above the terrain: from below, rows that look up are the expensive ones)
-		if (P.cam[2] > std::fmax(P.c0[2], P.c1[2]) && !std::getenv("HMRM_NO_BATCH"))
+		if (P.cam[2] > std::fmax(P.c0[2], P.c1[2]) && !c->knobs.no_batch)
 			P.batch_from_tile = (unsigned)slot.row_sky_first * (unsigned)P.tiles_x;
-		if (std::getenv("HMRM_DEBUG_SCHED"))
+		if (c->knobs.debug_sched)
 			std::fprintf(stderr, "sched: tiles_y %d sky_first %d batch_from %u n_tiles %d\n", P.tiles_y, slot.row_sky_first,
 			             P.batch_from_tile, P.tiles_x * P.tiles_y);
-	}
-
-	// FP32 miss prefilter (see ray_setup.cuh:fast_miss): the box inflated by 2^-12 of the scene scale
-	P.fast_setup = (f->precision == HMRM_FP32_FAST) ? 1 : 0;
-	{
-		const bool relative = f->projection != HMRM_ORTHOGRAPHIC;      // bounds relative to the camera position
-		double scale = 0.0;
-		for (int i = 0; i < 3; ++i) {
-			scale = std::fmax(scale, std::fmax(std::fabs(P.c0[i]), std::fabs(P.c1[i])));
-			scale = std::fmax(scale, std::fabs(P.cam[i]));
-			scale = std::fmax(scale, std::fabs(P.ul[i]) + std::fabs(P.pr[i]) + std::fabs(P.pd[i]));
-		}
-		const double delta = std::ldexp(scale, -12);
-		for (int i = 0; i < 3; ++i) {
-			const double lo = std::fmin(P.c0[i], P.c1[i]) - delta, hi = std::fmax(P.c0[i], P.c1[i]) + delta;
-			const double org = relative ? P.cam[i] : 0.0;
-			P.fs_b0[i] = (float)(lo - org);
-			P.fs_b1[i] = (float)(hi - org);
-			P.fs_ul[i] = (float)P.ul[i];
-			P.fs_pr[i] = (float)P.pr[i];
-			P.fs_pd[i] = (float)P.pd[i];
-		}
-		if (!std::isfinite(scale) || !(delta > 0.0)) P.fast_setup = 0;
 	}
 
 	P.surf = c->d_surf;
 	P.color = c->d_color;
 	P.fb = d_out;
+	P.pixel_format = f->pixel_format;
+	P.rgb_words = (W % 4) == 0 ? 1 : 0;
 	P.bg[0] = f->bg[0];
 	P.bg[1] = f->bg[1];
 	P.bg[2] = f->bg[2];
@@ -443,17 +476,32 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 
 	const bool want_stats = (f->flags & HMRM_FLAG_STATS) != 0;
 	const bool want_steps = (f->flags & HMRM_FLAG_STEP_INDEX) != 0;
+	const bool want_dump = (f->flags & HMRM_FLAG_RAY_DUMP) != 0;
+	// per-launch-slot outputs: the slot's previous kernel has finished (ev_end above), so growing them is safe while
+	// other frames of this context are still in flight on other streams
 	if (want_steps) {
 		const size_t need = (size_t)W * (size_t)H;
-		if (need > c->step_index_cap) {
-			HMRM_CUDA(c, cudaStreamSynchronize(stream));
-			cudaFree(c->d_step_index);
-			c->d_step_index = NULL;
-			HMRM_CUDA(c, cudaMalloc(&c->d_step_index, need * 4));
-			c->step_index_cap = need;
+		if (need > slot.step_cap) {
+			cudaFree(slot.d_step_index);
+			slot.d_step_index = NULL;
+			slot.step_cap = 0;
+			HMRM_CUDA(c, cudaMalloc(&slot.d_step_index, need * 4));
+			slot.step_cap = need;
 		}
-		HMRM_CUDA(c, cudaMemsetAsync(c->d_step_index, 0xFD, need * 4, stream));   // -3 = not rendered... bytes FD
-		P.step_index = c->d_step_index;
+		HMRM_CUDA(c, cudaMemsetAsync(slot.d_step_index, 0xFD, need * 4, stream));   // -3 = not rendered... bytes FD
+		P.step_index = slot.d_step_index;
+	}
+	if (want_dump) {
+		const size_t need = (size_t)W * (size_t)H;
+		if (need > slot.dump_cap) {
+			cudaFree(slot.d_ray_dump);
+			slot.d_ray_dump = NULL;
+			slot.dump_cap = 0;
+			HMRM_CUDA(c, cudaMalloc(&slot.d_ray_dump, need * 80));
+			slot.dump_cap = need;
+		}
+		HMRM_CUDA(c, cudaMemsetAsync(slot.d_ray_dump, 0xFF, need * 80, stream));    // NaN = not rendered
+		P.ray_dump = slot.d_ray_dump;
 	}
 	P.stats = slot.d_stats;
 	P.tile_counter = slot.d_tile_counter;
@@ -486,27 +534,24 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		const double step_cells = f->step_dist / f->grid_width;
 		int lmin = 1;
 		while (lmin < P.ltop && (double)(1 << lmin) < step_cells) lmin += 1;
-		// tuning knobs for experiments (never affect results, only how many fetches are issued)
-		const char *e_bias = std::getenv("HMRM_LMIN_BIAS"), *e_stride = std::getenv("HMRM_LSTRIDE");
-		const char *e_exit = std::getenv("HMRM_CELL_EXIT"), *e_start = std::getenv("HMRM_LSTART");
-		if (e_bias) lmin += std::atoi(e_bias);
+		// tuning knobs for experiments (never affect results, only how many fetches are issued): read once, hmrm_create
+		lmin += c->knobs.lmin_bias;
 		if (lmin < 1) lmin = 1;
 		if (lmin > P.ltop) lmin = P.ltop;
 		P.lmin = lmin;
-		P.lstride = e_stride ? std::atoi(e_stride) : 1;
-		if (P.lstride < 1) P.lstride = 1;
-		P.cell_exit_scale = e_exit ? (float)std::atof(e_exit) : 8.0f;
-		const char *e_climb = std::getenv("HMRM_CLIMB");
-		P.climb_ratio = e_climb ? (float)std::atof(e_climb) : 4.0f;
-		const int lstart = lmin + (e_start ? std::atoi(e_start) : 6) * P.lstride;
+		P.lstride = c->knobs.lstride < 1 ? 1 : c->knobs.lstride;
+		P.cell_exit_scale = c->knobs.cell_exit;
+		P.climb_ratio = c->knobs.climb;
+		const int lstart = lmin + c->knobs.lstart * P.lstride;
 		P.lstart = lstart > P.ltop ? P.ltop : (lstart < lmin ? lmin : lstart);
 		if (P.fx_bits < 1) traversal = HMRM_TRAVERSAL_BRUTE;
 		P.lv = c->d_mip;
 		P.lv_total = (unsigned long long)(c->mip_offset[c->mip_levels - 1] +
-		                                  (size_t)c->mip_w[c->mip_levels - 1] * (size_t)c->mip_h[c->mip_levels - 1]);
+		                                  pyr_level_elems(c->layout, c->mip_w[c->mip_levels - 1], c->mip_h[c->mip_levels - 1]));
+		P.layout = c->layout;
 		for (int l = 0; l < 16; ++l) {
 			P.lv_desc[l].x = (l < c->mip_levels) ? (unsigned)c->mip_offset[l] : 0u;
-			P.lv_desc[l].y = (l < c->mip_levels) ? (unsigned)c->mip_w[l] : 0u;
+			P.lv_desc[l].y = (l < c->mip_levels) ? pyr_level_pitch(c->layout, c->mip_w[l]) : 0u;
 		}
 		if (!std::isfinite(P.fx_scale)) traversal = HMRM_TRAVERSAL_BRUTE;
 	}
@@ -521,33 +566,27 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	(void)timed;
 	HMRM_CUDA(c, cudaEventRecord(slot.ev_begin, stream));
 	if (traversal == HMRM_TRAVERSAL_SKIP) {
-		const bool stats_kernel = want_stats || want_steps;
+		const bool stats_kernel = want_stats || want_steps || want_dump;
 		const int lin_warps = HMRM_LIN_THREADS / 32;
 		int lin_blocks = c->num_sms * HMRM_LIN_CTAS;
 		if (lin_blocks > (n_tiles + lin_warps - 1) / lin_warps) lin_blocks = (n_tiles + lin_warps - 1) / lin_warps;
 		if (lin_blocks < 1) lin_blocks = 1;
-		if (P.fast_setup) {
-			if (stats_kernel) k2_render_lin<true, true><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);
-			else k2_render_lin<false, true><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);
-		}
-		else {
-			if (stats_kernel) k2_render_lin<true, false><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);
-			else k2_render_lin<false, false><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);
-		}
+#define HMRM_LAUNCH_LIN(LAYOUT)                                                                              \
+		do {                                                                                                 \
+			if (stats_kernel) k2_render_lin<true, LAYOUT><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);   \
+			else k2_render_lin<false, LAYOUT><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);               \
+		} while (0)
+		if (c->layout == HMRM_LAYOUT_TILE4) HMRM_LAUNCH_LIN(kLayoutTile4);
+		else if (c->layout == HMRM_LAYOUT_ZORDER) HMRM_LAUNCH_LIN(kLayoutZOrder);
+		else HMRM_LAUNCH_LIN(kLayoutRowMajor);
+#undef HMRM_LAUNCH_LIN
 	}
 	else if (traversal == HMRM_TRAVERSAL_SKIP_FP64) {
-		const bool stats_kernel = want_stats || want_steps;
-		if (P.fast_setup) {
-			if (stats_kernel) k2_render_skip<true, true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
-			else k2_render_skip<false, true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
-		}
-		else {
-			if (stats_kernel) k2_render_skip<true, false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
-			else k2_render_skip<false, false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
-		}
+		if (want_stats || want_steps || want_dump) k2_render_skip<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		else k2_render_skip<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
 	}
 	else {
-		if (want_stats) k2_render_brute<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
+		if (want_stats || want_dump) k2_render_brute<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);
 		else k2_render_brute<false><<<blocks, warps_per_block * 32, 0, stream>>>(P);
 	}
 	HMRM_CUDA(c, cudaGetLastError());
@@ -558,6 +597,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	c->last_stream = stream;
 	c->last_had_stats = want_stats;
 	c->last_had_step_index = want_steps;
+	c->last_had_ray_dump = want_dump;
 	c->timing_valid = timed;
 	c->last_w = W;
 	c->last_h = H;
@@ -568,7 +608,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 // ranks may fill one shared, registered host frame, each over its own PCIe link): one strided copy + the ragged last
 // tile row.  Enqueued on the copy stream.
 int enqueue_copy_out(hmrm_ctx *c, const hmrm_frame *f, const uint32_t *fb, uint8_t *rgba_out, int rb, int re) {
-	const size_t row_bytes = (size_t)f->screen_width * 4;
+	const size_t row_bytes = (size_t)f->screen_width * (f->pixel_format == HMRM_PIXEL_RGB8 ? 3 : 4);
 	if (f->band_count > 1) {
 		const int tile_rows = (re - rb + 3) / 4;
 		const int owned = tile_rows > f->band_index ? (tile_rows - f->band_index + f->band_count - 1) / f->band_count : 0;
@@ -627,6 +667,30 @@ int hmrm_create(int device, hmrm_ctx **out) {
 
 	hmrm_ctx *c = new hmrm_ctx();
 	c->device = device;
+	{
+		// experiment knobs: the environment is read here and nowhere else
+		Knobs &k = c->knobs;
+		const char *e;
+		k.no_row_order = std::getenv("HMRM_NO_ROW_ORDER") != NULL;
+		k.no_batch = std::getenv("HMRM_NO_BATCH") != NULL;
+		k.debug_sched = std::getenv("HMRM_DEBUG_SCHED") != NULL;
+		k.lmin_bias = (e = std::getenv("HMRM_LMIN_BIAS")) ? std::atoi(e) : 0;
+		k.lstride = (e = std::getenv("HMRM_LSTRIDE")) ? std::atoi(e) : 1;
+		k.lstart = (e = std::getenv("HMRM_LSTART")) ? std::atoi(e) : 6;
+		k.cell_exit = (e = std::getenv("HMRM_CELL_EXIT")) ? (float)std::atof(e) : 8.0f;
+		k.climb = (e = std::getenv("HMRM_CLIMB")) ? (float)std::atof(e) : 4.0f;
+		k.zq_shrink_set = (e = std::getenv("HMRM_ZQ_RANGE_SHRINK")) != NULL;
+		k.zq_shrink = e ? std::atof(e) : 1.0;
+		k.peer_timeout_ns = (unsigned long long)((e = std::getenv("HMRM_PEER_TIMEOUT_MS")) ? std::atof(e) : 5000.0) * 1000000ULL;
+		c->layout_wanted = HMRM_LAYOUT_DEFAULT;
+		if ((e = std::getenv("HMRM_LAYOUT")) != NULL) {
+			if (!std::strcmp(e, "rowmajor")) c->layout_wanted = HMRM_LAYOUT_ROWMAJOR;
+			else if (!std::strcmp(e, "tile4")) c->layout_wanted = HMRM_LAYOUT_TILE4;
+			else if (!std::strcmp(e, "zorder")) c->layout_wanted = HMRM_LAYOUT_ZORDER;
+		}
+		c->layout = c->layout_wanted;
+	}
+	c->d_k1_counter = NULL;
 	c->num_sms = prop.multiProcessorCount;
 	c->stream = NULL;
 	for (int i = 0; i < kFrameRing; ++i) c->ring_stream[i] = NULL;
@@ -660,11 +724,10 @@ int hmrm_create(int device, hmrm_ctx **out) {
 	c->fb_w = c->fb_h = 0;
 	c->copy_stream = NULL;
 	c->slot = 0;
-	c->d_step_index = NULL;
-	c->step_index_cap = 0;
+	c->fb_format = HMRM_PIXEL_RGBA8;
 
 	c->launch_next = c->launch_last = 0;
-	c->last_had_stats = c->last_had_step_index = c->timing_valid = false;
+	c->last_had_stats = c->last_had_step_index = c->last_had_ray_dump = c->timing_valid = false;
 	c->last_w = c->last_h = 0;
 	c->last_stream = NULL;
 
@@ -683,6 +746,8 @@ int hmrm_create(int device, hmrm_ctx **out) {
 		if (err == cudaSuccess) err = cudaMalloc(&c->slots[i].d_tile_counter, 256);
 	}
 	if (err == cudaSuccess) err = cudaMalloc(&c->d_max_bits, 32);
+	if (err == cudaSuccess) err = cudaMalloc(&c->d_k1_counter, 256);
+	if (err == cudaSuccess) err = cudaMemset(c->d_k1_counter, 0, 256);
 	if (err != cudaSuccess) {
 		fail(NULL, HMRM_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(err));
 		hmrm_destroy(c);
@@ -700,6 +765,7 @@ void hmrm_destroy(hmrm_ctx *c) {
 	}
 	free_maps(c);
 	cudaFree(c->d_max_bits);
+	cudaFree(c->d_k1_counter);
 	cudaFree(c->d_wtab);
 	cudaFree(c->d_htab);
 
@@ -710,9 +776,10 @@ void hmrm_destroy(hmrm_ctx *c) {
 		if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
 	}
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
-	cudaFree(c->d_step_index);
 	for (int i = 0; i < kLaunchSlots; ++i) {
 		LaunchSlot &sl = c->slots[i];
+		cudaFree(sl.d_step_index);
+		cudaFree(sl.d_ray_dump);
 		cudaFree(sl.d_stats);
 		cudaFree(sl.d_tile_counter);
 		cudaFree(sl.d_sph);
@@ -806,9 +873,9 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 	c->min_surf = from_ordered_bits(bits[1]);
 
 	// Zq: sampled surf range [min_surf, max_surf] -> [2000, 63000] of the 16-bit scale; values outside clamp (and tie)
-	if (const char *shrink = std::getenv("HMRM_ZQ_RANGE_SHRINK")) {
+	if (c->knobs.zq_shrink_set) {
 		// test hook: pretend the sampled range was (much) too narrow, so that most values clamp and tie
-		const double f = std::atof(shrink), mid = 0.5 * (c->max_surf + c->min_surf), half = 0.5 * (c->max_surf - c->min_surf);
+		const double f = c->knobs.zq_shrink, mid = 0.5 * (c->max_surf + c->min_surf), half = 0.5 * (c->max_surf - c->min_surf);
 		c->min_surf = mid - f * half;
 		c->max_surf = mid + f * half;
 	}
@@ -816,13 +883,19 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 	c->zq_scale = (range > 0.0 && std::isfinite(range) && std::isfinite(61000.0 / range)) ? 61000.0 / range : 1.0;
 	c->zq_offset = HMRM_MAGIC + (2000.0 - c->min_surf * c->zq_scale);
 
-	// (2) fused build of surf, level 0 and the plain max-mip levels 1, 2; (3) remaining levels; (4) 3x3 dilation
+	// layout of the pyramid the traversal reads (pyramid_layout.cuh); the buffer was sized for any of them
+	c->layout = c->layout_wanted;
+	layout_pyramid(c, c->layout);
+
+	// (2) fused build of surf, level 0 and the plain max-mip levels 1, 2; (3) plain levels >= 3 in one launch;
+	// (4) the 3x3 dilation of every level >= 1, written in the traversal's layout, in one launch
 	{
 		uint16_t *plain1 = c->mip_levels > 1 ? c->d_dil : NULL;
-		uint16_t *plain2 = c->mip_levels > 2 ? c->d_dil + (c->mip_offset[2] - c->mip_offset[1]) : NULL;
+		uint16_t *plain2 = c->mip_levels > 2 ? c->d_dil + c->plain_offset[2] : NULL;
 		if (plain1) {
 			k1_build<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, c->map_w, c->map_h, q, c->zq_scale, c->zq_offset,
-			                                                 c->d_surf, c->d_mip, plain1, c->mip_w[1], plain2,
+			                                                 c->d_surf, c->d_mip, c->layout,
+			                                                 pyr_level_pitch(c->layout, c->map_w), plain1, c->mip_w[1], plain2,
 			                                                 c->mip_levels > 2 ? c->mip_w[2] : 0);
 		}
 		else {
@@ -833,15 +906,42 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 		}
 		HMRM_CUDA(c, cudaGetLastError());
 	}
-	for (int l = 1; l < c->mip_levels; ++l) {
-		uint16_t *plain = c->d_dil + (c->mip_offset[l] - c->mip_offset[1]);
-		if (l >= 3) {
-			const uint16_t *below = c->d_dil + (c->mip_offset[l - 1] - c->mip_offset[1]);
-			k1_mip_reduce<<<c->num_sms * 8, 256, 0, c->stream>>>(below, c->mip_w[l - 1], c->mip_h[l - 1], plain, c->mip_w[l],
-			                                                      c->mip_h[l]);
-			HMRM_CUDA(c, cudaGetLastError());
+	if (c->mip_levels > 3) {
+		MipJob job;
+		std::memset(&job, 0, sizeof job);
+		job.n_levels = c->mip_levels;
+		for (int l = 0; l < c->mip_levels; ++l) {
+			job.w[l] = c->mip_w[l];
+			job.h[l] = c->mip_h[l];
+			job.plain_off[l] = (unsigned)c->plain_offset[l];
 		}
-		k1_mip_dilate<<<c->num_sms * 8, 256, 0, c->stream>>>(plain, c->d_mip + c->mip_offset[l], c->mip_w[l], c->mip_h[l]);
+		const int regions = ((c->mip_w[2] + 127) / 128) * ((c->mip_h[2] + 127) / 128);
+		k1_mip_upper<<<regions, 256, 0, c->stream>>>(c->d_dil, job, c->d_k1_counter);
+		HMRM_CUDA(c, cudaGetLastError());
+	}
+	if (c->mip_levels > 1) {
+		DilateJob job;
+		std::memset(&job, 0, sizeof job);
+		job.n_levels = c->mip_levels;
+		job.layout = c->layout;
+		unsigned long long items = 0;
+		job.first_item[0] = job.first_item[1] = 0;
+		for (int l = 0; l < c->mip_levels; ++l) {
+			job.w[l] = c->mip_w[l];
+			job.h[l] = c->mip_h[l];
+			job.plain_off[l] = (unsigned)c->plain_offset[l];
+			job.dst_off[l] = (unsigned)c->mip_offset[l];
+			job.dst_pitch[l] = pyr_level_pitch(c->layout, c->mip_w[l]);
+			if (l >= 1) {
+				job.first_item[l] = items;
+				items += (unsigned long long)((c->mip_w[l] + 3) / 4) * (unsigned long long)c->mip_h[l];
+			}
+			job.first_item[l + 1] = items;
+		}
+		unsigned long long want = (items + 255) / 256;
+		const unsigned long long cap_blocks = (unsigned long long)c->num_sms * 16ULL;
+		const int blocks = (int)std::max(1ULL, std::min(want, cap_blocks));
+		k1_dilate_levels<<<blocks, 256, 0, c->stream>>>(c->d_dil, c->d_mip, job);
 		HMRM_CUDA(c, cudaGetLastError());
 	}
 	HMRM_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -912,17 +1012,22 @@ int hmrm_render_async(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
 	if (f->screen_width < 2 || f->screen_height < 2 || f->screen_width > 65536 || f->screen_height > 65536)
 		return fail(c, HMRM_ERR_INVALID, "resolution %dx%d outside [2,65536]", f->screen_width, f->screen_height);
 	HMRM_CUDA(c, cudaSetDevice(c->device));
-	int rc = ensure_framebuffer(c, f->screen_width, f->screen_height);
+	if (f->pixel_format != HMRM_PIXEL_RGBA8 && f->pixel_format != HMRM_PIXEL_RGB8)
+		return fail(c, HMRM_ERR_INVALID, "unknown pixel_format %d", (int)f->pixel_format);
+	int rc = ensure_framebuffer(c, f->screen_width, f->screen_height, f->pixel_format);
 	if (rc) return rc;
 	// Whole frames (cycle_period 1) rotate through kFrameRing device buffers so that the copy-out of frame n overlaps
 	// the kernels of frames n+1 and n+2; the progressive interleave (cycle_period > 1) accumulates in the one
 	// persistent buffer.  Each buffer has its own compute stream, so the kernel of the next frame starts filling SMs as
 	// the CTAs of this one run out of tiles (a handful of grazing tiles take ~50x the mean: the tail of a frame
 	// leaves most SMs idle).
-	const bool whole = f->cycle_period == 1 && (f->flags & HMRM_FLAG_STEP_INDEX) == 0;
+	const bool whole = f->cycle_period == 1 && (f->flags & (HMRM_FLAG_STEP_INDEX | HMRM_FLAG_RAY_DUMP)) == 0;
 	const int slot = whole ? (c->slot + 1) % kFrameRing : 0;
 	uint32_t *fb = c->d_fb[slot];
 	cudaStream_t cs = c->ring_stream[slot];
+	// nothing may be written into this buffer (by the kernel, or by the copy below) while an earlier frame is still
+	// being copied out of it
+	if (c->copy_pending[slot]) HMRM_CUDA(c, cudaStreamWaitEvent(cs, c->ev_copied[slot], 0));
 	if (!whole) {
 		// progressive frames and step-index captures are ordered after everything else
 		for (int i = 1; i < kFrameRing; ++i) HMRM_CUDA(c, cudaStreamSynchronize(c->ring_stream[i]));
@@ -932,7 +1037,6 @@ int hmrm_render_async(hmrm_ctx *c, const hmrm_frame *f, uint8_t *rgba_out) {
 			                             cudaMemcpyDeviceToDevice, cs));
 		}
 	}
-	if (c->copy_pending[slot]) HMRM_CUDA(c, cudaStreamWaitEvent(cs, c->ev_copied[slot], 0));
 	int rb = f->row_begin, re = f->row_end;
 	if (rb == 0 && re == 0) re = f->screen_height;
 	// (Rendering a frame that finds the pipeline idle as four interleaved bands, each copied out as soon as its kernel
@@ -1019,8 +1123,51 @@ int hmrm_get_step_index(hmrm_ctx *c, int32_t *step_index) {
 	if (!c->last_had_step_index) return fail(c, HMRM_ERR_STATE, "last render did not set HMRM_FLAG_STEP_INDEX");
 	HMRM_CUDA(c, cudaSetDevice(c->device));
 	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
-	HMRM_CUDA(c, cudaMemcpy(step_index, c->d_step_index, (size_t)c->last_w * (size_t)c->last_h * 4,
+	HMRM_CUDA(c, cudaMemcpy(step_index, c->slots[c->launch_last].d_step_index, (size_t)c->last_w * (size_t)c->last_h * 4,
 	                        cudaMemcpyDeviceToHost));
+	return HMRM_OK;
+}
+
+int hmrm_get_ray_dump(hmrm_ctx *c, double *out) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!out) return fail(c, HMRM_ERR_INVALID, "out is NULL");
+	if (!c->last_had_ray_dump) return fail(c, HMRM_ERR_STATE, "last render did not set HMRM_FLAG_RAY_DUMP");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	HMRM_CUDA(c, cudaStreamSynchronize(c->last_stream ? c->last_stream : c->stream));
+	HMRM_CUDA(c, cudaMemcpy(out, c->slots[c->launch_last].d_ray_dump, (size_t)c->last_w * (size_t)c->last_h * 80,
+	                        cudaMemcpyDeviceToHost));
+	return HMRM_OK;
+}
+
+int hmrm_set_layout(hmrm_ctx *c, int layout) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (layout != HMRM_LAYOUT_ROWMAJOR && layout != HMRM_LAYOUT_TILE4 && layout != HMRM_LAYOUT_ZORDER)
+		return fail(c, HMRM_ERR_INVALID, "unknown layout %d", layout);
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	if (int rc = drain(c)) return rc;
+	if (layout != c->layout) c->heights_set = false;      // the pyramid must be rebuilt: hmrm_update_heightmap
+	c->layout_wanted = layout;
+	return HMRM_OK;
+}
+
+int hmrm_get_layout(hmrm_ctx *c) { return c ? c->layout_wanted : -1; }
+
+int hmrm_debug_aabb(hmrm_ctx *c, int32_t n, const double *rays, const double *boxes, double *out) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (n < 1 || !rays || !boxes || !out) return fail(c, HMRM_ERR_INVALID, "hmrm_debug_aabb: bad arguments");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	double *d = NULL;
+	HMRM_CUDA(c, cudaMalloc(&d, (size_t)n * 17 * sizeof(double)));
+	cudaError_t e = cudaMemcpy(d, rays, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) e = cudaMemcpy(d + (size_t)n * 6, boxes, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice);
+	if (e == cudaSuccess) {
+		k_debug_aabb<<<(n + 127) / 128, 128, 0, c->stream>>>(n, d, d + (size_t)n * 6, d + (size_t)n * 12);
+		e = cudaGetLastError();
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	if (e == cudaSuccess) e = cudaMemcpy(out, d + (size_t)n * 12, (size_t)n * 5 * sizeof(double), cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	if (e != cudaSuccess) return fail(c, HMRM_ERR_CUDA, "hmrm_debug_aabb: %s", cudaGetErrorString(e));
 	return HMRM_OK;
 }
 
@@ -1049,6 +1196,15 @@ int hmrm_host_alloc(void **ptr, size_t bytes) {
 	*ptr = NULL;
 	cudaError_t e = cudaMallocHost(ptr, bytes);
 	if (e != cudaSuccess) return fail(NULL, HMRM_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+	return HMRM_OK;
+}
+
+int hmrm_host_alloc_flags(void **ptr, size_t bytes, uint32_t flags) {
+	if (!ptr || (flags & ~(uint32_t)HMRM_HOST_WRITE_COMBINED)) return HMRM_ERR_INVALID;
+	*ptr = NULL;
+	const unsigned cf = cudaHostAllocPortable | ((flags & HMRM_HOST_WRITE_COMBINED) ? cudaHostAllocWriteCombined : 0u);
+	cudaError_t e = cudaHostAlloc(ptr, bytes, cf);
+	if (e != cudaSuccess) return fail(NULL, HMRM_ERR_CUDA, "cudaHostAlloc(%zu, %u) failed: %s", bytes, cf, cudaGetErrorString(e));
 	return HMRM_OK;
 }
 
@@ -1106,6 +1262,54 @@ int hmrm_ipc_open(hmrm_ctx *c, const uint8_t handle[HMRM_IPC_HANDLE_BYTES], void
 	std::memcpy(&h, handle, sizeof h);
 	// maps the exporting device's memory into this process and enables peer access to it (NVLink / NVSwitch)
 	HMRM_CUDA(c, cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+	return HMRM_OK;
+}
+
+int hmrm_render_peer(hmrm_ctx *c, const hmrm_frame *f, void *d_frame, void *d_ctrl, uint32_t use, void *stream) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!d_frame || !d_ctrl || use == 0u) return fail(c, HMRM_ERR_INVALID, "hmrm_render_peer: bad arguments");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+	PeerCtrl *ctrl = (PeerCtrl *)d_ctrl;
+	// the buffer may be overwritten once the root has read its previous use
+	k_peer_spin<<<1, 1, 0, s>>>(&ctrl->released, use - 1u, &ctrl->error, c->knobs.peer_timeout_ns);
+	HMRM_CUDA(c, cudaGetLastError());
+	const int rc = enqueue_render(c, f, (uint32_t *)d_frame, s, true);
+	if (rc) return rc;
+	k_peer_signal<<<1, 1, 0, s>>>(&ctrl->arrived);
+	HMRM_CUDA(c, cudaGetLastError());
+	return HMRM_OK;
+}
+
+int hmrm_peer_wait(hmrm_ctx *c, void *d_ctrl, uint32_t use, int32_t ranks, void *stream) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!d_ctrl || use == 0u || ranks < 1) return fail(c, HMRM_ERR_INVALID, "hmrm_peer_wait: bad arguments");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	PeerCtrl *ctrl = (PeerCtrl *)d_ctrl;
+	k_peer_spin<<<1, 1, 0, stream ? (cudaStream_t)stream : c->stream>>>(&ctrl->arrived, use * (uint32_t)ranks, &ctrl->error,
+	                                                                     c->knobs.peer_timeout_ns);
+	HMRM_CUDA(c, cudaGetLastError());
+	return HMRM_OK;
+}
+
+int hmrm_peer_release(hmrm_ctx *c, void *d_ctrl, uint32_t use, void *stream) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!d_ctrl) return fail(c, HMRM_ERR_INVALID, "hmrm_peer_release: bad arguments");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	k_peer_release<<<1, 1, 0, stream ? (cudaStream_t)stream : c->stream>>>(&((PeerCtrl *)d_ctrl)->released, use);
+	HMRM_CUDA(c, cudaGetLastError());
+	return HMRM_OK;
+}
+
+int hmrm_peer_status(hmrm_ctx *c, void *d_ctrl, uint32_t out[3]) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!d_ctrl || !out) return fail(c, HMRM_ERR_INVALID, "hmrm_peer_status: bad arguments");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	PeerCtrl h;
+	HMRM_CUDA(c, cudaMemcpy(&h, d_ctrl, sizeof h, cudaMemcpyDeviceToHost));
+	out[0] = h.arrived;
+	out[1] = h.released;
+	out[2] = h.error;
 	return HMRM_OK;
 }
 

@@ -11,6 +11,7 @@
 #define HMRM_K1_PREPASS_CUH
 
 #include "device_math.cuh"
+#include "pyramid_layout.cuh"
 
 namespace hmrm {
 
@@ -145,7 +146,8 @@ __global__ void __launch_bounds__(256) k1_range(const uint8_t *__restrict__ rgb8
 // and the plain max-mip levels 1 and 2 of that block.  HBM-bound: 3 B in, 8 + 2 + 0.5 + 0.125 B out per cell.
 __global__ void __launch_bounds__(256) k1_build(const uint8_t *__restrict__ rgb8, int w, int h, PrepassParams q,
                                                 double zq_scale, double zq_offset, double *__restrict__ surf,
-                                                uint16_t *__restrict__ lv0, uint16_t *__restrict__ plain1, int w1,
+                                                uint16_t *__restrict__ lv0, int layout, unsigned pitch0,
+                                                uint16_t *__restrict__ plain1, int w1,
                                                 uint16_t *__restrict__ plain2, int w2) {
 	const int tiles_x = (w + 3) / 4, tiles_y = (h + 3) / 4;
 	const long long n_tiles = (long long)tiles_x * tiles_y;
@@ -166,6 +168,9 @@ __global__ void __launch_bounds__(256) k1_build(const uint8_t *__restrict__ rgb8
 		const int bx = (int)(t % tiles_x), by = (int)(t / tiles_x);
 		const int x0 = bx * 4, y0 = by * 4;
 		int m1[2][2] = {{0, 0}, {0, 0}};
+		// tiled layouts: this thread's 4x4 cells are one 32-byte sector of level 0 (pyramid_layout.cuh)
+		const bool sector_store = vec && layout != kLayoutRowMajor;
+		uint2 zrow[4] = {{0u, 0u}, {0u, 0u}, {0u, 0u}, {0u, 0u}};
 #pragma unroll
 		for (int j = 0; j < 4; ++j) {
 			const int y = y0 + j;
@@ -214,14 +219,21 @@ __global__ void __launch_bounds__(256) k1_build(const uint8_t *__restrict__ rgb8
 				double2 *sp = (double2 *)(surf + row);
 				sp[0] = make_double2(s[0], s[1]);
 				sp[1] = make_double2(s[2], s[3]);
-				*(uint2 *)(lv0 + row) = make_uint2((unsigned)zq[0] | ((unsigned)zq[1] << 16), (unsigned)zq[2] | ((unsigned)zq[3] << 16));
+				const uint2 packed = make_uint2((unsigned)zq[0] | ((unsigned)zq[1] << 16), (unsigned)zq[2] | ((unsigned)zq[3] << 16));
+				if (sector_store) zrow[j] = packed;
+				else *(uint2 *)(lv0 + row) = packed;
 			}
 			else {
 				for (int i = 0; i < valid; ++i) {
 					surf[row + i] = s[i];
-					lv0[row + i] = (uint16_t)zq[i];
+					lv0[pyr_index_rt(layout, (unsigned)(x0 + i), (unsigned)y, pitch0)] = (uint16_t)zq[i];
 				}
 			}
+		}
+		if (sector_store) {
+			uint4 *sp = (uint4 *)(lv0 + pyr_index_rt(layout, (unsigned)x0, (unsigned)y0, pitch0));
+			sp[0] = make_uint4(zrow[0].x, zrow[0].y, zrow[1].x, zrow[1].y);
+			sp[1] = make_uint4(zrow[2].x, zrow[2].y, zrow[3].x, zrow[3].y);
 		}
 		// plain level 1: 2x2 texels of this block (those that exist), level 2: one texel
 		const int h1 = (h + 1) / 2;
@@ -248,67 +260,150 @@ __global__ void __launch_bounds__(256) k1_quantise(const double *__restrict__ su
 	}
 }
 
-// dst[y][x] = max of the 2x2 block of src (clipped at the edges): one mip level
-__global__ void __launch_bounds__(256) k1_mip_reduce(const uint16_t *__restrict__ src, int sw, int sh,
-                                                     uint16_t *__restrict__ dst, int dw, int dh) {
-	const long long n = (long long)dw * dh;
-	const long long stride = (long long)gridDim.x * blockDim.x;
-	for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-		const int x = (int)(p % dw), y = (int)(p / dw);
-		const int x0 = 2 * x, y0 = 2 * y;
-		const int x1 = (x0 + 1 < sw) ? x0 + 1 : x0, y1 = (y0 + 1 < sh) ? y0 + 1 : y0;
-		const uint16_t a = src[(size_t)y0 * sw + x0], b = src[(size_t)y0 * sw + x1];
-		const uint16_t c = src[(size_t)y1 * sw + x0], d = src[(size_t)y1 * sw + x1];
-		const uint16_t ab = a > b ? a : b, cd = c > d ? c : d;
-		dst[p] = ab > cd ? ab : cd;
+// ---- plain max-mip levels >= 3 in ONE launch --------------------------------------------------------------
+//
+// Level l texel (X, Y) = max of level l-1 texels (2X, 2Y) .. (2X+1, 2Y+1), clipped at the edges.  A CTA owns a
+// 128 x 128 region of plain level 2 and reduces it in shared memory to its 64 x 64 texels of level 3, 32 x 32 of
+// level 4, ... 1 texel of level 9 (region edges are multiples of 2^7, so the texels of those levels nest inside
+// regions).  The last CTA to finish (global counter) reduces the few remaining levels (>= 10, at most 64 x 64
+// texels of input) on its own.  Heights are unsigned, so missing texels are 0 and every reduction is a plain max.
+struct MipJob {
+	int n_levels;                 // levels 0 .. n_levels-1 exist
+	int w[16], h[16];
+	unsigned plain_off[16];       // element offset of plain level l inside the scratch (l >= 1)
+};
+
+__global__ void __launch_bounds__(256) k1_mip_upper(uint16_t *__restrict__ plain, MipJob job, unsigned int *done_counter) {
+	__shared__ unsigned short s_a[64 * 64];
+	__shared__ unsigned short s_b[32 * 32];
+	__shared__ bool s_last;
+	const int w2 = job.w[2], h2 = job.h[2];
+	const int regions_x = (w2 + 127) / 128;
+	const int rx = (int)(blockIdx.x % (unsigned)regions_x), ry = (int)(blockIdx.x / (unsigned)regions_x);
+	const uint16_t *p2 = plain + job.plain_off[2];
+	// level 3 of this region from plain level 2 (global)
+	for (int t = threadIdx.x; t < 64 * 64; t += blockDim.x) {
+		const int lx = t & 63, ly = t >> 6;
+		const int x0 = rx * 128 + 2 * lx, y0 = ry * 128 + 2 * ly;
+		unsigned m = 0u;
+		if (y0 < h2) {
+			if (x0 < w2) m = __ldg(p2 + (size_t)y0 * w2 + x0);
+			if (x0 + 1 < w2) m = max(m, (unsigned)__ldg(p2 + (size_t)y0 * w2 + x0 + 1));
+		}
+		if (y0 + 1 < h2) {
+			if (x0 < w2) m = max(m, (unsigned)__ldg(p2 + (size_t)(y0 + 1) * w2 + x0));
+			if (x0 + 1 < w2) m = max(m, (unsigned)__ldg(p2 + (size_t)(y0 + 1) * w2 + x0 + 1));
+		}
+		s_a[t] = (unsigned short)m;
+		const int X = rx * 64 + lx, Y = ry * 64 + ly;
+		if (job.n_levels > 3 && X < job.w[3] && Y < job.h[3]) plain[job.plain_off[3] + (size_t)Y * job.w[3] + X] = (uint16_t)m;
 	}
+	__syncthreads();
+	// levels 4 .. 9 inside shared memory, ping-pong between the two arrays
+	unsigned short *src = s_a, *dst = s_b;
+	int side = 64;
+	for (int l = 4; l <= 9 && l < job.n_levels; ++l) {
+		const int half = side >> 1;
+		for (int t = threadIdx.x; t < half * half; t += blockDim.x) {
+			const int lx = t % half, ly = t / half;
+			const unsigned a = src[(2 * ly) * side + 2 * lx], b = src[(2 * ly) * side + 2 * lx + 1];
+			const unsigned c = src[(2 * ly + 1) * side + 2 * lx], d = src[(2 * ly + 1) * side + 2 * lx + 1];
+			const unsigned m = max(max(a, b), max(c, d));
+			dst[ly * half + lx] = (unsigned short)m;
+			const int X = rx * half + lx, Y = ry * half + ly;
+			if (X < job.w[l] && Y < job.h[l]) plain[job.plain_off[l] + (size_t)Y * job.w[l] + X] = (uint16_t)m;
+		}
+		__syncthreads();
+		unsigned short *tmp = src; src = dst; dst = tmp;
+		side = half;
+	}
+	if (job.n_levels <= 10) return;
+	// the remaining levels: by the last CTA to arrive
+	__threadfence();
+	__syncthreads();
+	if (threadIdx.x == 0) s_last = atomicAdd(done_counter, 1u) == gridDim.x - 1u;
+	__syncthreads();
+	if (!s_last) return;
+	__threadfence();
+	for (int l = 10; l < job.n_levels; ++l) {
+		const int sw = job.w[l - 1], sh = job.h[l - 1], dw = job.w[l], dh = job.h[l];
+		const uint16_t *below = plain + job.plain_off[l - 1];
+		for (int t = threadIdx.x; t < dw * dh; t += blockDim.x) {
+			const int x = t % dw, y = t / dw;
+			const int x0 = 2 * x, y0 = 2 * y;
+			const int x1 = (x0 + 1 < sw) ? x0 + 1 : x0, y1 = (y0 + 1 < sh) ? y0 + 1 : y0;
+			const unsigned a = __ldcg(below + (size_t)y0 * sw + x0), b = __ldcg(below + (size_t)y0 * sw + x1);
+			const unsigned c = __ldcg(below + (size_t)y1 * sw + x0), d = __ldcg(below + (size_t)y1 * sw + x1);
+			plain[job.plain_off[l] + t] = (uint16_t)max(max(a, b), max(c, d));
+		}
+		__threadfence();
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *done_counter = 0u;
 }
 
-// dst[y][x] = max of src over the 3x3 neighbourhood (clipped): a sample that clears dst clears the block it is in
-// AND the eight blocks around it, so a jump may run on into the neighbouring blocks instead of stopping at an edge.
-__global__ void __launch_bounds__(256) k1_mip_dilate(const uint16_t *__restrict__ src, uint16_t *__restrict__ dst,
-                                                     int w, int h) {
-	const long long stride = (long long)gridDim.x * blockDim.x;
-	if ((w & 3) == 0) {
-		// four outputs per thread: per input row one 8-byte load plus the two horizontal neighbours
-		const int wq = w / 4;
-		const long long nq = (long long)wq * h;
-		for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nq; t += stride) {
-			const int xq = (int)(t % wq), y = (int)(t / wq);
-			const int x = xq * 4;
-			unsigned o0 = 0, o1 = 0, o2 = 0, o3 = 0;
-			for (int dy = -1; dy <= 1; ++dy) {
-				const int yy = y + dy;
-				if (yy < 0 || yy >= h) continue;
-				const uint16_t *row = src + (size_t)yy * w;
-				const uint2 v = __ldg((const uint2 *)(row + x));
-				const unsigned c0 = v.x & 0xFFFFu, c1 = v.x >> 16, c2 = v.y & 0xFFFFu, c3 = v.y >> 16;
-				const unsigned l = x > 0 ? (unsigned)__ldg(row + x - 1) : 0u;
-				const unsigned r = x + 4 < w ? (unsigned)__ldg(row + x + 4) : 0u;
-				o0 = max(o0, max(l, max(c0, c1)));
-				o1 = max(o1, max(c0, max(c1, c2)));
-				o2 = max(o2, max(c1, max(c2, c3)));
-				o3 = max(o3, max(c2, max(c3, r)));
-			}
-			*(uint2 *)(dst + (size_t)y * w + x) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
-		}
-		return;
-	}
-	const long long n = (long long)w * h;
-	for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
-		const int x = (int)(p % w), y = (int)(p / w);
-		uint16_t m = 0;
+// ---- 3x3 dilation of every level >= 1 in ONE launch, written in the traversal's layout ---------------------
+//
+// dst(l)[y][x] = max of plain(l) over the 3x3 neighbourhood (clipped): a sample that clears dst clears the block it
+// is in AND the eight blocks around it, so a jump may run on into the neighbouring blocks instead of stopping at an
+// edge.  Work item = four horizontally adjacent outputs (x multiple of 4): in the tiled layouts those are contiguous.
+struct DilateJob {
+	int n_levels;
+	int layout;
+	int w[16], h[16];
+	unsigned plain_off[16];       // source: plain level l in the scratch (row-major)
+	unsigned dst_off[16];         // destination: level l in the pyramid the traversal reads
+	unsigned dst_pitch[16];
+	unsigned long long first_item[17];   // work items of level l are [first_item[l], first_item[l+1]); level 0 has none
+};
+
+__global__ void __launch_bounds__(256) k1_dilate_levels(const uint16_t *__restrict__ plain, uint16_t *__restrict__ pyr, DilateJob job) {
+	const unsigned long long total = job.first_item[job.n_levels];
+	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+	for (unsigned long long item = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
+		int l = 1;
+		while (l + 1 < job.n_levels && item >= job.first_item[l + 1]) l += 1;
+		const int w = job.w[l], h = job.h[l], wq = (w + 3) / 4;
+		const unsigned long long t = item - job.first_item[l];
+		const int xq = (int)(t % (unsigned)wq), y = (int)(t / (unsigned)wq);
+		const int x = xq * 4;
+		const uint16_t *src = plain + job.plain_off[l];
+		unsigned o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+		const bool vec = (w & 3) == 0;
 		for (int dy = -1; dy <= 1; ++dy) {
 			const int yy = y + dy;
 			if (yy < 0 || yy >= h) continue;
-			for (int dx = -1; dx <= 1; ++dx) {
-				const int xx = x + dx;
-				if (xx < 0 || xx >= w) continue;
-				const uint16_t v = src[(size_t)yy * w + xx];
-				m = v > m ? v : m;
+			const uint16_t *row = src + (size_t)yy * w;
+			unsigned c0, c1, c2, c3;
+			if (vec) {
+				const uint2 v = __ldg((const uint2 *)(row + x));
+				c0 = v.x & 0xFFFFu; c1 = v.x >> 16; c2 = v.y & 0xFFFFu; c3 = v.y >> 16;
 			}
+			else {
+				c0 = __ldg(row + x);
+				c1 = x + 1 < w ? (unsigned)__ldg(row + x + 1) : 0u;
+				c2 = x + 2 < w ? (unsigned)__ldg(row + x + 2) : 0u;
+				c3 = x + 3 < w ? (unsigned)__ldg(row + x + 3) : 0u;
+			}
+			const unsigned lft = x > 0 ? (unsigned)__ldg(row + x - 1) : 0u;
+			const unsigned rgt = x + 4 < w ? (unsigned)__ldg(row + x + 4) : 0u;
+			o0 = max(o0, max(lft, max(c0, c1)));
+			o1 = max(o1, max(c0, max(c1, c2)));
+			o2 = max(o2, max(c1, max(c2, c3)));
+			o3 = max(o3, max(c2, max(c3, rgt)));
 		}
-		dst[p] = m;
+		uint16_t *dst = pyr + job.dst_off[l];
+		const unsigned at = pyr_index_rt(job.layout, (unsigned)x, (unsigned)y, job.dst_pitch[l]);
+		if (vec || job.layout != kLayoutRowMajor) {
+			// row-major with w % 4 == 0, or a tiled layout (rows of a sector are 4 texels, padded): one 8-byte store
+			*(uint2 *)(dst + at) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+		}
+		else {
+			dst[at] = (uint16_t)o0;
+			if (x + 1 < w) dst[at + 1] = (uint16_t)o1;
+			if (x + 2 < w) dst[at + 2] = (uint16_t)o2;
+			if (x + 3 < w) dst[at + 3] = (uint16_t)o3;
+		}
 	}
 }
 

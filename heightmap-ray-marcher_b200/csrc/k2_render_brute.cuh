@@ -86,13 +86,15 @@ __global__ void __launch_bounds__(256) k2_render_brute(const __grid_constant__ R
 		const bool active = pixel_selected(P, px, py);
 
 		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u, {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};
+		uint32_t rgba = 0u;
 		if (active) {
 			const Ray ray = generate_ray(P, px, py);
-			uint32_t rgba = 0u;
 			bool real_hit = false;
 			int first_hit = -1;
-			double x, y, z;
-			if (box_entry(P, ray, x, y, z)) {
+			double x, y, z, lo = 0.0;
+			const bool entered = box_entry(P, ray, x, y, z, lo);
+			if (kStats && P.ray_dump) dump_ray(P, px, py, ray, entered, lo, x, y, z);
+			if (entered) {
 				tally.box_hit = 1u;
 				first_hit = -2;
 				x = fadd(x, fmul(P.nudge, ray.dx));               // main/hmap.cpp:998
@@ -129,9 +131,9 @@ __global__ void __launch_bounds__(256) k2_render_brute(const __grid_constant__ R
 			}
 			if (!real_hit) rgba = miss_colour(P, ray.dz);
 			else tally.surf_hit = 1u;
-			P.fb[HMRM_CHECKED(P, (size_t)py * (size_t)P.W + (size_t)px, (size_t)P.W * (size_t)P.H)] = rgba;   // SetPixel, main/hmap.cpp:139-154
 			if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
 		}
+		store_pixel(P, px, py, active, rgba);            // SetPixel, main/hmap.cpp:139-154
 		commit_tally<kStats>(P, active, tally);
 	}
 }

@@ -110,7 +110,7 @@ __device__ __forceinline__ bool lin_slope(double s_units, long long &d) {
 	return true;
 }
 
-template <bool kStats>
+template <bool kStats, int kLayout>
 __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray, double ex, double ey, double ez,
                                           unsigned &hit_cell, bool &real_hit, int &first_hit, PixelTally &tally) {
 	const int k = P.fx_bits;
@@ -165,7 +165,7 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 
 	auto probe = [&](int lvl, int vx, int vy) -> int {   // dilated block maximum, in the z units of the model
 		const uint2 d = P.lv_desc[lvl];
-		const unsigned idx = d.x + (unsigned)(vy >> (k + lvl)) * d.y + (unsigned)(vx >> (k + lvl));
+		const unsigned idx = d.x + pyr_index<kLayout>((unsigned)(vx >> (k + lvl)), (unsigned)(vy >> (k + lvl)), d.y);
 		return (int)__ldg(P.lv + HMRM_CHECKED(P, idx, P.lv_total));
 	};
 	// `above q` / `below q` with the model's error (< 1.6/16 Zq) and Zq16's rounding (ties at q +- 1/2) covered
@@ -398,7 +398,7 @@ next_sample:
 	tally.fetches = fetches;
 }
 
-template <bool kStats, bool kFast>
+template <bool kStats, int kLayout>
 __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin(const __grid_constant__ RenderParams P) {
 	const int lane = threadIdx.x & 31;
 	const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
@@ -431,28 +431,28 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin
 		const bool active = pixel_selected(P, px, py);
 
 		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u, {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};
+		uint32_t rgba = 0u;
 		if (active) {
-			uint32_t rgba = 0u;
 			bool real_hit = false;
 			int first_hit = -1;
 			unsigned hit_cell = 0u;
-			if (!(kFast && fast_miss(P, px, py, rgba))) {
-				const Ray ray = generate_ray(P, px, py);
-				double ex, ey, ez;
-				if (box_entry(P, ray, ex, ey, ez)) {
-					tally.box_hit = 1u;
-					first_hit = -2;
-					march_lin<kStats>(P, ray, ex, ey, ez, hit_cell, real_hit, first_hit, tally);
-				}
-				if (!real_hit) rgba = miss_colour(P, ray.dz);
-				else {
-					rgba = hit_colour(P, __ldg(P.color + HMRM_CHECKED(P, hit_cell, (size_t)P.map_w * (size_t)P.map_h)));
-					tally.surf_hit = 1u;
-				}
+			const Ray ray = generate_ray(P, px, py);
+			double ex, ey, ez, lo = 0.0;
+			const bool entered = box_entry(P, ray, ex, ey, ez, lo);
+			if (kStats && P.ray_dump) dump_ray(P, px, py, ray, entered, lo, ex, ey, ez);
+			if (entered) {
+				tally.box_hit = 1u;
+				first_hit = -2;
+				march_lin<kStats, kLayout>(P, ray, ex, ey, ez, hit_cell, real_hit, first_hit, tally);
 			}
-			P.fb[HMRM_CHECKED(P, (size_t)py * (size_t)P.W + (size_t)px, (size_t)P.W * (size_t)P.H)] = rgba;
+			if (!real_hit) rgba = miss_colour(P, ray.dz);
+			else {
+				rgba = hit_colour(P, __ldg(P.color + HMRM_CHECKED(P, hit_cell, (size_t)P.map_w * (size_t)P.map_h)));
+				tally.surf_hit = 1u;
+			}
 			if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
 		}
+		store_pixel(P, px, py, active, rgba);       // main/hmap.cpp:139-154 (RGBA8), or packed RGB8
 		commit_tally<kStats>(P, active, tally);
 	}
 }

@@ -162,7 +162,7 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 	// hold the maximum over the 2^l-cell block and its eight neighbours
 	auto probe = [&](int level, int vx, int vy) -> int {
 		const uint2 d = P.lv_desc[level];
-		const unsigned idx = d.x + (unsigned)(vy >> (k + level)) * d.y + (unsigned)(vx >> (k + level));
+		const unsigned idx = d.x + pyr_index_rt(P.layout, (unsigned)(vx >> (k + level)), (unsigned)(vy >> (k + level)), d.y);
 		return (int)__ldg(P.lv + HMRM_CHECKED(P, idx, P.lv_total));
 	};
 	// extent (clipped to the grid) of the neighbourhood a level-`level` texel covers, in fixed-point units
@@ -315,9 +315,7 @@ __device__ __forceinline__ void march_skip(const RenderParams &P, const Ray &ray
 	if (kStats) atomicMax(&P.stats->dbg[10], (unsigned long long)iters);    // most loop iterations of any ray
 }
 
-// kFast: HMRM_FP32_FAST front end (ray_setup.cuh:fast_miss) — a separate instantiation, because merging the filter
-// into the exact kernel behind a run-time flag made ptxas spill in the march loop (terrain frames 0.79 -> 1.5 ms).
-template <bool kStats, bool kFast>
+template <bool kStats>
 __global__ void __launch_bounds__(256, 4) k2_render_skip(const __grid_constant__ RenderParams P) {
 	const int lane = threadIdx.x & 31;
 	const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
@@ -336,24 +334,24 @@ __global__ void __launch_bounds__(256, 4) k2_render_skip(const __grid_constant__
 		if (kStats) t_tile = clock64();
 
 		PixelTally tally = {0ULL, 0ULL, 0u, 0u, 0u, {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u}};
+		uint32_t rgba = 0u;
 		if (active) {
-			uint32_t rgba = 0u;
 			bool real_hit = false;
 			int first_hit = -1;
-			if (!(kFast && fast_miss(P, px, py, rgba))) {
-				const Ray ray = generate_ray(P, px, py);
-				double ex, ey, ez;
-				if (box_entry(P, ray, ex, ey, ez)) {
-					tally.box_hit = 1u;
-					first_hit = -2;
-					march_skip<kStats>(P, ray, ex, ey, ez, rgba, real_hit, first_hit, tally);
-				}
-				if (!real_hit) rgba = miss_colour(P, ray.dz);
-				else tally.surf_hit = 1u;
+			const Ray ray = generate_ray(P, px, py);
+			double ex, ey, ez, lo = 0.0;
+			const bool entered = box_entry(P, ray, ex, ey, ez, lo);
+			if (kStats && P.ray_dump) dump_ray(P, px, py, ray, entered, lo, ex, ey, ez);
+			if (entered) {
+				tally.box_hit = 1u;
+				first_hit = -2;
+				march_skip<kStats>(P, ray, ex, ey, ez, rgba, real_hit, first_hit, tally);
 			}
-			P.fb[HMRM_CHECKED(P, (size_t)py * (size_t)P.W + (size_t)px, (size_t)P.W * (size_t)P.H)] = rgba;
+			if (!real_hit) rgba = miss_colour(P, ray.dz);
+			else tally.surf_hit = 1u;
 			if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
 		}
+		store_pixel(P, px, py, active, rgba);
 		commit_tally<kStats>(P, active, tally);
 		if (kStats && lane == 0) {
 			const unsigned long long dt = (unsigned long long)(clock64() - t_tile);

@@ -71,21 +71,28 @@ __device__ __forceinline__ bool slab_axis(double c0, double c1, double o, double
 	return true;
 }
 
-// intersection(): true and the entry point when the ray enters the box at a distance d with 0 <= d < inf.
-__device__ __forceinline__ bool box_entry(const RenderParams &P, const Ray &r, double &ex, double &ey, double &ez) {
-	double lo = -__longlong_as_double(0x7FF0000000000000LL);
-	double hi = __longlong_as_double(0x7FF0000000000000LL);
-	if (!slab_axis(P.c0[0], P.c1[0], r.ox, r.dx, lo, hi)) return false;
-	if (!slab_axis(P.c0[1], P.c1[1], r.oy, r.dy, lo, hi)) return false;
-	if (!slab_axis(P.c0[2], P.c1[2], r.oz, r.dz, lo, hi)) return false;
+// distance() + intersection() (src/AABB.cpp:30-77): `dist` is what distance() returns (+inf when a slab test fails
+// or lo > hi, else the entry distance lo); true and the entry point when 0 <= dist < inf.
+__device__ __forceinline__ bool box_entry_at(const double *c0, const double *c1, const Ray &r, double &ex, double &ey,
+                                             double &ez, double &dist) {
+	const double inf = __longlong_as_double(0x7FF0000000000000LL);
+	double lo = -inf, hi = inf;
+	dist = inf;
+	if (!slab_axis(c0[0], c1[0], r.ox, r.dx, lo, hi)) return false;
+	if (!slab_axis(c0[1], c1[1], r.oy, r.dy, lo, hi)) return false;
+	if (!slab_axis(c0[2], c1[2], r.oz, r.dz, lo, hi)) return false;
 	if (lo > hi) return false;
-	// d == +inf cannot be reached here with lo <= hi unless hi is inf too; keep the reference's tests
-	if (lo == __longlong_as_double(0x7FF0000000000000LL)) return false;
+	dist = lo;
+	if (lo == inf) return false;
 	if (lo < 0.0) return false;
 	ex = fadd(r.ox, fmul(lo, r.dx));
 	ey = fadd(r.oy, fmul(lo, r.dy));
 	ez = fadd(r.oz, fmul(lo, r.dz));
 	return true;
+}
+
+__device__ __forceinline__ bool box_entry(const RenderParams &P, const Ray &r, double &ex, double &ey, double &ez, double &dist) {
+	return box_entry_at(P.c0, P.c1, r, ex, ey, ez, dist);
 }
 
 __device__ __forceinline__ uint32_t sky_channel(double v) {
@@ -111,93 +118,51 @@ __device__ __forceinline__ uint32_t hit_colour(const RenderParams &P, uint32_t t
 	return ((texel >> 24) == 0u) ? P.bg_rgba : (texel | 0xFF000000u);
 }
 
-// ---- FP32 prefilter for rays that miss the box (HMRM_FP32_FAST) ---------------------------------------------
-//
-// Most rays of a frame never touch the terrain box; for them the exact front end (six FP64 divides for the slab
-// test, a square root and a divide for the normalisation) only has to deliver (a) the verdict "miss" and (b) the
-// sky colour.  This filter decides both in FP32 when it can PROVE the FP64 result, and otherwise says "unknown"
-// and the exact path runs.  It never changes a pixel:
-//  (a) the slab test is run against the box inflated by fs_delta = 2^-12 x (scene scale) — about 10^3 times the
-//      worst FP32 evaluation error and 10^9 times the reference's own FP64 rounding — so "misses the inflated box
-//      in FP32" implies "the reference's FP64 comparison chain reports a miss".  Rays with a near-zero direction
-//      component (inf/NaN territory of src/AABB.cpp:58-59) are left to the exact path.
-//  (b) the colour channels floor(clamp(220 z^2 + bg)) etc. (main/hmap.cpp:1044-1051) are taken from FP32 only
-//      when the value is at least 3e-4 away from the next integer; z comes from the exactly computed FP64 ray
-//      vector with one float rsqrt (relative error < 3e-7 => channel error < 1.5e-4).
-__device__ __forceinline__ float approx_rcp(float x) {
-	float r;
-	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-	return r;
-}
-__device__ __forceinline__ float approx_rsqrt(float x) {
-	float r;
-	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-	return r;
+// HMRM_FLAG_RAY_DUMP: the device's own intermediates of this pixel, for bit-pattern comparison with the reference's
+// GetRay / distance / intersection (src/Perspective.cpp:25-32, src/AABB.cpp:30-77): frames are blind to ulp errors.
+// Record = pos[3], dir[3], distance() as the reference returns it, entry[3] (zeros when intersection() is false).
+__device__ __noinline__ void dump_ray(const RenderParams &P, int px, int py, const Ray &r, bool entered, double lo,
+                                      double ex, double ey, double ez) {
+	double *o = P.ray_dump + ((size_t)py * (size_t)P.W + (size_t)px) * 10;
+	o[0] = r.ox; o[1] = r.oy; o[2] = r.oz;
+	o[3] = r.dx; o[4] = r.dy; o[5] = r.dz;
+	o[6] = lo;
+	o[7] = entered ? ex : 0.0;
+	o[8] = entered ? ey : 0.0;
+	o[9] = entered ? ez : 0.0;
 }
 
-__device__ __forceinline__ bool fast_channel(float c, uint32_t &out) {
-	if (c >= 255.001f) { out = 255u; return true; }
-	const float fl = floorf(c);
-	const float d = c - fl;
-	out = (uint32_t)fl;
-	return d > 3.0e-4f && d < 1.0f - 3.0e-4f && c < 254.999f;
-}
-
-// true: the pixel is a proven miss and `rgba` is its (proven) colour.  false: run the exact path.
-__device__ __forceinline__ bool fast_miss(const RenderParams &P, int px, int py, uint32_t &rgba) {
-	float vx, vy, vz;          // ray direction (any length)
-	float ox = 0.f, oy = 0.f, oz = 0.f;   // ray origin relative to the frame of fs_b0/fs_b1
-	double dz_exact = 0.0;     // spherical / orthographic: the exact z of the unit direction is already at hand
-	double vzd = 0.0, len2d = 1.0;
-	if (P.projection == 1) {
-		const double w = __ldg(P.wtab + px), h = __ldg(P.htab + py);
-		const double dx = fsub(fadd(fadd(P.ul[0], fmul(w, P.pr[0])), fmul(h, P.pd[0])), P.cam[0]);
-		const double dy = fsub(fadd(fadd(P.ul[1], fmul(w, P.pr[1])), fmul(h, P.pd[1])), P.cam[1]);
-		vzd = fsub(fadd(fadd(P.ul[2], fmul(w, P.pr[2])), fmul(h, P.pd[2])), P.cam[2]);
-		len2d = fadd(fadd(fmul(dx, dx), fmul(dy, dy)), fmul(vzd, vzd));
-		vx = (float)dx; vy = (float)dy; vz = (float)vzd;
+// SetPixel (main/hmap.cpp:139-154).  Called by the whole warp (8x4-pixel tile, lane = 8 * row + column); `active`
+// lanes own a pixel of this frame.  RGBA8: one 32-bit store per pixel, A = 255.  RGB8 (HMRM_PIXEL_RGB8: the alpha
+// byte is always 255 in the reference, so it is dead weight on PCIe / NVLink): a tile row is 24 contiguous bytes;
+// when all 8 pixels of the row are written and rows are 4-byte aligned, lanes 0..5 of the row assemble them as six
+// 32-bit words from their neighbours' colours (two shuffles), otherwise every lane stores its 3 bytes.
+__device__ __forceinline__ void store_pixel(const RenderParams &P, int px, int py, bool active, uint32_t rgba) {
+	if (P.pixel_format == 0) {
+		if (active) P.fb[HMRM_CHECKED(P, (size_t)py * (size_t)P.W + (size_t)px, (size_t)P.W * (size_t)P.H)] = rgba;
+		return;
 	}
-	else if (P.projection == 2) {
-		const float sv = (float)__ldg(P.sin_va + py);
-		vx = sv * (float)__ldg(P.cos_ha + px);
-		vy = sv * (float)__ldg(P.sin_ha + px);
-		dz_exact = __ldg(P.cos_va + py);
-		vz = (float)dz_exact;
+	const int lane = threadIdx.x & 31, i = lane & 7;
+	const unsigned full = __ballot_sync(0xFFFFFFFFu, active);
+	const bool row_full = ((full >> (lane & 24)) & 0xFFu) == 0xFFu && P.rgb_words;
+	const int a = (i * 4) / 3;                         // first pixel contributing to word i (i < 6): 0 1 2 4 5 6
+	const uint32_t A = __shfl_sync(0xFFFFFFFFu, rgba, (lane & 24) | min(a, 7)) & 0xFFFFFFu;
+	const uint32_t B = __shfl_sync(0xFFFFFFFFu, rgba, (lane & 24) | min(a + 1, 7)) & 0xFFFFFFu;
+	uint8_t *fb8 = (uint8_t *)P.fb;
+	if (row_full) {
+		if (i < 6) {
+			const int sh = 8 * ((i * 4) % 3);
+			const uint32_t word = (A >> sh) | (B << (24 - sh));
+			const size_t at = ((size_t)py * (size_t)P.W + (size_t)(px & ~7)) * 3;   // multiple of 4 (W % 4 == 0)
+			*(uint32_t *)(fb8 + HMRM_CHECKED(P, at + (size_t)i * 4, (size_t)P.W * (size_t)P.H * 3)) = word;
+		}
 	}
-	else {
-		const float w = (float)__ldg(P.wtab + px), h = (float)__ldg(P.htab + py);
-		ox = fmaf(h, P.fs_pd[0], fmaf(w, P.fs_pr[0], P.fs_ul[0]));
-		oy = fmaf(h, P.fs_pd[1], fmaf(w, P.fs_pr[1], P.fs_ul[1]));
-		oz = fmaf(h, P.fs_pd[2], fmaf(w, P.fs_pr[2], P.fs_ul[2]));
-		vx = (float)P.look[0]; vy = (float)P.look[1]; vz = (float)P.look[2];
-		dz_exact = P.look[2];
+	else if (active) {
+		uint8_t *o = fb8 + HMRM_CHECKED(P, ((size_t)py * (size_t)P.W + (size_t)px) * 3, (size_t)P.W * (size_t)P.H * 3);
+		o[0] = (uint8_t)rgba;
+		o[1] = (uint8_t)(rgba >> 8);
+		o[2] = (uint8_t)(rgba >> 16);
 	}
-	const float ax = fabsf(vx), ay = fabsf(vy), az = fabsf(vz);
-	const float vmax = fmaxf(ax, fmaxf(ay, az));
-	if (!(fminf(ax, fminf(ay, az)) > vmax * 1.0e-6f) || !(vmax < 1.0e18f)) return false;
-
-	const float rx = approx_rcp(vx), ry = approx_rcp(vy), rz = approx_rcp(vz);
-	const float tx0 = (P.fs_b0[0] - ox) * rx, tx1 = (P.fs_b1[0] - ox) * rx;
-	const float ty0 = (P.fs_b0[1] - oy) * ry, ty1 = (P.fs_b1[1] - oy) * ry;
-	const float tz0 = (P.fs_b0[2] - oz) * rz, tz1 = (P.fs_b1[2] - oz) * rz;
-	const float lo = fmaxf(fminf(tx0, tx1), fmaxf(fminf(ty0, ty1), fminf(tz0, tz1)));
-	const float hi = fminf(fmaxf(tx0, tx1), fminf(fmaxf(ty0, ty1), fmaxf(tz0, tz1)));
-	if (!((lo > hi) || (hi < 0.0f))) return false;      // may touch the (inflated) box: exact path
-
-	if (P.projection != 1) {
-		rgba = miss_colour(P, dz_exact);                   // exact, and cheap: no normalisation needed
-		return true;
-	}
-	const float zf = (float)vzd * approx_rsqrt((float)len2d);
-	if (fabsf(zf) < 1.0e-5f) return false;                // sign of dir.z not provable
-	if (zf < 0.0f) { rgba = P.bg_rgba; return true; }
-	const float zz = zf * zf;
-	uint32_t r, g, b;
-	const bool ok = fast_channel(fmaf(220.0f, zz, (float)P.bg[0]), r) & fast_channel(fmaf(240.0f, zz, (float)P.bg[1]), g) &
-	                fast_channel(fmaf(255.0f, zf, (float)P.bg[2]), b);
-	if (!ok) return false;
-	rgba = r | (g << 8) | (b << 16) | 0xFF000000u;
-	return true;
 }
 
 } // namespace hmrm

@@ -53,8 +53,11 @@ struct RenderParams {
 	const double *surf;            // fl(height + min_height), row-major [map_h][map_w]
 	const uint32_t *color;         // RGBA8 little-endian, row-major
 	// outputs
-	uint32_t *fb;                  // RGBA8 [H][W]
+	uint32_t *fb;                  // RGBA8 [H][W], or packed RGB8 [H][W][3] (pixel_format 1)
+	int pixel_format;              // HMRM_PIXEL_RGBA8 (0) / HMRM_PIXEL_RGB8 (1)
+	int rgb_words;                 // RGB8: rows are 4-byte aligned (W % 4 == 0) -> tile rows go out as 32-bit words
 	int32_t *step_index;           // optional [H][W]
+	double *ray_dump;              // optional [H][W][10] (HMRM_FLAG_RAY_DUMP, ray_setup.cuh:dump_ray)
 	DeviceStats *stats;            // optional
 	unsigned int *tile_counter;    // persistent-thread tile queue head
 	// ---- skip traversal (k2_render_skip.cuh): fixed-point view of the march ----
@@ -64,13 +67,10 @@ struct RenderParams {
 	int lmin, lstride, ltop;       // mip levels used this frame: lmin, lmin+lstride, ... <= ltop (0 = cell test)
 	int lstart;                    // level of a ray's first test
 	float cell_exit_scale;         // leave cell-by-cell mode when Zq(z) - q exceeds this many steps of descent
-	const uint16_t *lv;            // all levels back to back: level 0 = Zq(surf) per cell (row-major [map_h][map_w]),
-	                               // level l >= 1 = max of level 0 over the 2^l x 2^l block and its eight neighbours
-	uint2 lv_desc[16];             // per level: (element offset into lv, row pitch)
-	// ---- FP32 miss prefilter (HMRM_FP32_FAST): slab bounds of the box inflated by 2^-12 of the scene scale ----
-	int fast_setup;                // 0 = off (pure FP64 front end)
-	float fs_b0[3], fs_b1[3];      // inflated box, b0 < b1 per axis; relative to cam for perspective / spherical
-	float fs_ul[3], fs_pr[3], fs_pd[3];   // orthographic ray origin plane, as floats
+	const uint16_t *lv;            // all levels back to back: level 0 = Zq(surf) per cell, level l >= 1 = max of level 0
+	                               // over the 2^l x 2^l block and its eight neighbours; texel order per `layout`
+	int layout;                    // pyramid_layout.cuh (the lin kernel takes it as a template parameter)
+	uint2 lv_desc[16];             // per level: (element offset into lv, layout's pitch term)
 	uint32_t bg_rgba;              // bg colour with alpha 255
 	uint8_t bg[3];
 	uint8_t pad;

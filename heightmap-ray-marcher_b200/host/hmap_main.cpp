@@ -108,7 +108,8 @@ hmrm_frame make_frame(const Config &cfg, const Options &opt) {
 	f.cycle = 0;
 	f.cycle_period = 1;
 	f.traversal = opt.traversal;
-	f.flags = HMRM_FLAG_STATS;
+	// counting costs per-warp atomics: only when the caller asked for the numbers (the cut-off status is always reported)
+	f.flags = opt.stats_json.empty() ? 0u : HMRM_FLAG_STATS;
 	return f;
 }
 

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define HMRM_ABI_VERSION 1
+#define HMRM_ABI_VERSION 2
 
 /* image_plane values, main/hmap.cpp:104-107 */
 #define HMRM_PERSPECTIVE  1
@@ -31,9 +31,11 @@ extern "C" {
 
 /* arithmetic mode of the render kernel */
 #define HMRM_FP64_EXACT 0   /* bit-exact to the reference's RGBA8 framebuffer */
-#define HMRM_FP32_FAST  1   /* FP32 front-end filter for rays that provably miss the box; the tolerance of the north
-                             * star is >= 99.5 % identical pixels, |step delta| <= 1 — by construction it changes none
-                             *  */
+#define HMRM_FP32_FAST  1   /* accepted, and an ALIAS of HMRM_FP64_EXACT: the production traversal already marches on a
+                             * 32/64-bit integer model and keeps FP64 for ray set-up and for the few samples the model
+                             * cannot decide, so there is nothing left for a lossy mode to win.
+                             * The north star's tolerance (>= 99.5 % identical pixels, |step delta| <= 1) is met
+                             * with 100 % / 0 and is written out in the tests. */
 
 /* traversal strategy (results are identical; this selects the kernel) */
 #define HMRM_TRAVERSAL_AUTO  0
@@ -44,6 +46,18 @@ extern "C" {
 /* hmrm_frame.flags */
 #define HMRM_FLAG_STATS      1u  /* count rays / steps / fetches (hmrm_get_stats) */
 #define HMRM_FLAG_STEP_INDEX 2u  /* record the per-pixel first-hit step index (hmrm_get_step_index) */
+#define HMRM_FLAG_RAY_DUMP   4u  /* record the device's ray / slab distance / entry point per pixel (hmrm_get_ray_dump) */
+
+/* hmrm_frame.pixel_format: layout of the frame the render calls write */
+#define HMRM_PIXEL_RGBA8 0       /* the reference's framebuf: [H][W][4], A = 255 (main/hmap.cpp:139-154) */
+#define HMRM_PIXEL_RGB8  1       /* the same pixels without the constant alpha byte: [H][W][3] (25 % fewer bytes over
+                                  * PCIe / NVLink; the north star's "RGB8 bands") */
+
+/* memory layout of the 16-bit height pyramid the march fetches from (csrc/pyramid_layout.cuh); results are identical */
+#define HMRM_LAYOUT_ROWMAJOR 0
+#define HMRM_LAYOUT_TILE4    1   /* 4x4-texel (32-byte sector) tiles, tiles in row-major order */
+#define HMRM_LAYOUT_ZORDER   2   /* 4x4-texel tiles in Z-order (Morton) inside 64x64-texel blocks */
+#define HMRM_LAYOUT_DEFAULT  HMRM_LAYOUT_TILE4
 
 #define HMRM_OK                  0
 #define HMRM_ERR_INVALID         1   /* bad argument */
@@ -68,7 +82,7 @@ typedef struct hmrm_frame {
 	double grid_width;      /* :65 */
 	double step_dist;       /* :68 */
 	uint8_t bg[3];          /* bg_r, bg_g, bg_b :110-112 */
-	uint8_t reserved0;
+	uint8_t pixel_format;   /* HMRM_PIXEL_RGBA8 (0, the reference's framebuf) | HMRM_PIXEL_RGB8 */
 	int32_t cycle;          /* first pixel index of this frame (:979), 0 <= cycle < cycle_period */
 	int32_t cycle_period;   /* pixel stride (:71,:980); 1 = full frame */
 	int32_t row_begin;      /* rows [row_begin,row_end) are rendered: row band of a multi-GPU frame */
@@ -108,6 +122,11 @@ int hmrm_set_maps_device(hmrm_ctx *ctx, const void *d_height_rgb8, const void *d
 int hmrm_synth_maps(hmrm_ctx *ctx, uint32_t log2n, uint32_t seed);
 int hmrm_get_maps(hmrm_ctx *ctx, uint8_t *height_rgb8, uint8_t *color_rgba8);   /* download (either may be NULL) */
 
+/* layout of the height pyramid (HMRM_LAYOUT_*; also the HMRM_LAYOUT environment variable at hmrm_create:
+ * rowmajor | tile4 | zorder).  Takes effect at the next hmrm_update_heightmap, which must follow. */
+int hmrm_set_layout(hmrm_ctx *ctx, int layout);
+int hmrm_get_layout(hmrm_ctx *ctx);
+
 /* ---- prepass: replaces UpdateHeightmap, main/hmap.cpp:171-191 (kernel K1) ---- */
 int hmrm_update_heightmap(hmrm_ctx *ctx, const double lum[3], double min_height, double max_height);
 /* heights exactly as the reference's heightmap_buf (double[H][W], main/hmap.cpp:53), for parity checks */
@@ -115,7 +134,8 @@ int hmrm_get_heights(hmrm_ctx *ctx, double *heights);
 
 /* ---- render: replaces main/hmap.cpp:952-1058 (ImagePlane ctor + pixel loop; kernel K2) ---- */
 void hmrm_frame_defaults(hmrm_frame *f);            /* the reference's defaults, :31-112, cycle_period 1 */
-/* rgba_out: host RGBA8 [screen_height][screen_width][4], stride W*4 — the reference's framebuf (:612).
+/* rgba_out: host RGBA8 [screen_height][screen_width][4], stride W*4 — the reference's framebuf (:612) — or, with
+ * pixel_format = HMRM_PIXEL_RGB8, [screen_height][screen_width][3], stride W*3.
  * Only the pixels selected by cycle/cycle_period and the row band are written. Synchronous. */
 int hmrm_render(hmrm_ctx *ctx, const hmrm_frame *f, uint8_t *rgba_out);
 /* device output (same layout) on `stream` (a cudaStream_t, NULL = ctx's own stream); asynchronous */
@@ -141,6 +161,11 @@ int hmrm_get_stats(hmrm_ctx *ctx, hmrm_stats *out);            /* of the last re
 int hmrm_get_debug_counters(hmrm_ctx *ctx, int64_t out[12]);
 int hmrm_get_step_index(hmrm_ctx *ctx, int32_t *step_index);   /* int32 [H][W]: first-hit sample index,
                                                                   -1 box missed, -2 no surface hit */
+/* of the last HMRM_FLAG_RAY_DUMP render: double [H][W][10] = what the DEVICE computed for each pixel: ray pos[3] and
+ * dir[3] (ImagePlane::GetRay, src/Perspective.cpp:25-32 etc.), the slab entry distance (distance(), src/AABB.cpp:49-77;
+ * -inf..inf as the reference leaves it when a slab test fails early), and the entry point (intersection(), :30-47; zeros
+ * when the box is missed).  Pixels not rendered by that frame are NaN. */
+int hmrm_get_ray_dump(hmrm_ctx *ctx, double *out);
 
 /* ---- type-level API mirror (host side; no device work) ---- */
 /* DegreesToRads, main/hmap.cpp:131-133 */
@@ -150,8 +175,16 @@ void hmrm_camera_basis(double hang, double vang, double look[3], double up[3]);
 /* ImagePlane::GetRay (src/ImagePlane.hpp:10) of the plane the frame describes; w,h in [0,1] */
 int hmrm_get_ray(const hmrm_frame *f, double w, double h, double pos[3], double dir[3]);
 
+/* The device's own slab test (the function the render kernels call; src/AABB.cpp:30-77) on n caller-supplied rays
+ * (pos[3], dir[3] each) and boxes (c0[3], c1[3] each): out[n][5] = distance(), intersection() as 0/1, entry point.
+ * For known-answer tests against the reference's functions. */
+int hmrm_debug_aabb(hmrm_ctx *ctx, int32_t n, const double *rays, const double *boxes, double *out);
+
 /* pinned host memory helpers (so that callers without a CUDA binding can stage buffers) */
 int hmrm_host_alloc(void **ptr, size_t bytes);
+/* the same with HMRM_HOST_* flags; write-combined memory is fast to fill from the device and slow to read on the CPU */
+#define HMRM_HOST_WRITE_COMBINED 1u
+int hmrm_host_alloc_flags(void **ptr, size_t bytes, uint32_t flags);
 void hmrm_host_free(void *ptr);
 /* page-lock memory the caller owns (e.g. a POSIX shared-memory frame that several ranks fill with their bands) */
 int hmrm_host_register(void *ptr, size_t bytes);
@@ -169,6 +202,22 @@ int hmrm_device_free(hmrm_ctx *ctx, void *dptr);
 int hmrm_ipc_export(hmrm_ctx *ctx, void *dptr, uint8_t handle[HMRM_IPC_HANDLE_BYTES]);   /* dptr from hmrm_device_alloc */
 int hmrm_ipc_open(hmrm_ctx *ctx, const uint8_t handle[HMRM_IPC_HANDLE_BYTES], void **dptr); /* in ANOTHER process */
 int hmrm_ipc_close(hmrm_ctx *ctx, void *dptr);
+
+/* Device-side completion of a peer frame (csrc/peer_sync.cuh): no collective, no host synchronisation.
+ * The root allocates frame bytes + HMRM_PEER_CTRL_BYTES with hmrm_device_alloc (zero-filled); the control block is the
+ * last HMRM_PEER_CTRL_BYTES of it (any 128-byte aligned place will do).  `use` counts the uses of ONE buffer, from 1.
+ *   every rank:  hmrm_render_peer(ctx, f, d_frame, d_ctrl, use, stream)   waits (on the device) until the root has
+ *                released use - 1, renders this rank's bands (f->band_count / band_index) into d_frame and counts the
+ *                rank as arrived;
+ *   the root:    hmrm_peer_wait(ctx, d_ctrl, use, ranks, stream)          stream-ordered: what follows on `stream`
+ *                sees the complete frame;  hmrm_peer_release(ctx, d_ctrl, use, stream) when it has been read.
+ * A wait that lasts longer than 5 s (HMRM_PEER_TIMEOUT_MS) sets the block's error word instead of hanging the GPU:
+ * hmrm_peer_status returns {arrived, released, error}. */
+#define HMRM_PEER_CTRL_BYTES 256
+int hmrm_render_peer(hmrm_ctx *ctx, const hmrm_frame *f, void *d_frame, void *d_ctrl, uint32_t use, void *stream);
+int hmrm_peer_wait(hmrm_ctx *ctx, void *d_ctrl, uint32_t use, int32_t ranks, void *stream);
+int hmrm_peer_release(hmrm_ctx *ctx, void *d_ctrl, uint32_t use, void *stream);
+int hmrm_peer_status(hmrm_ctx *ctx, void *d_ctrl, uint32_t out[3]);
 
 #ifdef __cplusplus
 }

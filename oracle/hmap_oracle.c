@@ -15,6 +15,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <string.h>
 #include <time.h>
 
 #include "../heightmap-ray-marcher_b200/csrc/synth_fbm.h"
@@ -196,10 +197,38 @@ static uint8_t sky_channel(double v) {
 
 #define ORACLE_STEP_CAP ((int64_t)1 << 31)
 
+/* Where the march reads the map from: the arrays the reference holds (heightmap_buf, colormap_buf), or — for maps
+ * too large to materialise on the test host (32768^2: 8 GiB of FP64 heights) — the procedural synthetic map itself:
+ * the texel's grey value v is generated on the fly and its height comes from a 256-entry table of UpdateHeightmap's
+ * expression for (v, v, v). */
+typedef struct map_source {
+	const double *heights;
+	const uint8_t *colormap;
+	int synth;
+	uint32_t log2n, seed;
+	double lut[256];
+} map_source;
+
+static inline double source_height(const map_source *m, int32_t gx, int32_t gy, size_t cell) {
+	if (!m->synth) return m->heights[cell];
+	return m->lut[hmrm_synth_height((uint32_t)gx, (uint32_t)gy, m->log2n, m->seed)];
+}
+
+static inline void source_texel(const map_source *m, int32_t gx, int32_t gy, size_t cell, uint8_t t[4]) {
+	if (!m->synth) {
+		const uint8_t *texel = m->colormap + cell * 4u;
+		t[0] = texel[0]; t[1] = texel[1]; t[2] = texel[2]; t[3] = texel[3];
+		return;
+	}
+	const uint32_t v = hmrm_synth_height((uint32_t)gx, (uint32_t)gy, m->log2n, m->seed);
+	const uint32_t c = hmrm_synth_color(v, (uint32_t)gx, (uint32_t)gy, 1u << m->log2n);
+	t[0] = (uint8_t)(c & 255u); t[1] = (uint8_t)((c >> 8) & 255u); t[2] = (uint8_t)((c >> 16) & 255u); t[3] = (uint8_t)(c >> 24);
+}
+
 /* main/hmap.cpp:952-1058 */
-int oracle_render(const oracle_frame *f, const double *heights, const uint8_t *colormap,
-                  int32_t map_w, int32_t map_h, uint8_t *framebuf, int32_t *step_index,
-                  int32_t row_begin, int32_t row_end, oracle_stats *stats) {
+static int render_core(const oracle_frame *f, const map_source *src,
+                       int32_t map_w, int32_t map_h, uint8_t *framebuf, int32_t *step_index,
+                       int32_t row_begin, int32_t row_end, oracle_stats *stats) {
 	const plane pl = plane_build(f);
 	const int32_t W = f->screen_width, H = f->screen_height;
 	const double gw = f->grid_width;
@@ -243,8 +272,9 @@ int oracle_render(const oracle_frame *f, const double *heights, const uint8_t *c
 				const int32_t gy = trunc_i32(-(y - c0[1]) / gw);          /* :1003-1004 */
 				if (gx < 0 || gy < 0 || gx >= map_w || gy >= map_h) break;
 				const size_t cell = (size_t)gx + (size_t)gy * (size_t)map_w;
-				if (z < heights[cell] + c0[2]) {                            /* :1016 */
-					const uint8_t *texel = colormap + cell * 4u;
+				if (z < source_height(src, gx, gy, cell) + c0[2]) {         /* :1016 */
+					uint8_t texel[4];
+					source_texel(src, gx, gy, cell, texel);
 					if (texel[3] == 0) { out[0] = f->bg[0]; out[1] = f->bg[1]; out[2] = f->bg[2]; }
 					else { out[0] = texel[0]; out[1] = texel[1]; out[2] = texel[2]; }
 					out[3] = 255;
@@ -285,6 +315,32 @@ int oracle_render(const oracle_frame *f, const double *heights, const uint8_t *c
 		stats->status = capped;
 	}
 	return capped;
+}
+
+int oracle_render(const oracle_frame *f, const double *heights, const uint8_t *colormap,
+                  int32_t map_w, int32_t map_h, uint8_t *framebuf, int32_t *step_index,
+                  int32_t row_begin, int32_t row_end, oracle_stats *stats) {
+	map_source src;
+	memset(&src, 0, sizeof src);
+	src.heights = heights;
+	src.colormap = colormap;
+	return render_core(f, &src, map_w, map_h, framebuf, step_index, row_begin, row_end, stats);
+}
+
+int oracle_render_synth(const oracle_frame *f, uint32_t log2n, uint32_t seed, double lum_r, double lum_g, double lum_b,
+                        uint8_t *framebuf, int32_t *step_index, int32_t row_begin, int32_t row_end,
+                        oracle_stats *stats) {
+	map_source src;
+	memset(&src, 0, sizeof src);
+	src.synth = 1;
+	src.log2n = log2n;
+	src.seed = seed;
+	for (int v = 0; v < 256; ++v) {
+		const uint8_t rgb[3] = {(uint8_t)v, (uint8_t)v, (uint8_t)v};
+		oracle_update_heightmap(rgb, 1, lum_r, lum_g, lum_b, f->min_height, f->max_height, &src.lut[v]);
+	}
+	const int32_t n = (int32_t)(1u << log2n);
+	return render_core(f, &src, n, n, framebuf, step_index, row_begin, row_end, stats);
 }
 
 void oracle_synth_maps(uint32_t log2n, uint32_t seed, uint8_t *height_rgb8, uint8_t *color_rgba8) {

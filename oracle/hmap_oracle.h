@@ -77,6 +77,13 @@ int oracle_render(const oracle_frame *f, const double *heights, const uint8_t *c
                   int32_t map_w, int32_t map_h, uint8_t *framebuf, int32_t *step_index,
                   int32_t row_begin, int32_t row_end, oracle_stats *stats);
 
+/* The same loop over the procedural synthetic map (csrc/synth_fbm.h) of size 2^log2n, texels generated on the fly:
+ * for map sizes whose FP64 height array does not fit the test host (BASELINE configs 3-5: 8192^2 .. 32768^2).
+ * Heights are UpdateHeightmap's expression (main/hmap.cpp:171-191) evaluated for the texel's grey value. */
+int oracle_render_synth(const oracle_frame *f, uint32_t log2n, uint32_t seed, double lum_r, double lum_g, double lum_b,
+                        uint8_t *framebuf, int32_t *step_index, int32_t row_begin, int32_t row_end,
+                        oracle_stats *stats);
+
 /* synthetic maps (csrc/synth_fbm.h) on the CPU: rgb8 [n][n][3], rgba8 [n][n][4] */
 void oracle_synth_maps(uint32_t log2n, uint32_t seed, uint8_t *height_rgb8, uint8_t *color_rgba8);
 

@@ -70,8 +70,7 @@ def build_oracle() -> None:
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not ORACLE_SO.exists():
-            build_oracle()
+        build_oracle()          # make: a no-op when oracle/_build/liboracle.so is newer than its sources
         L = C.CDLL(str(ORACLE_SO))
         L.oracle_deg2rad.restype = C.c_double
         L.oracle_deg2rad.argtypes = [C.c_double]
@@ -88,6 +87,10 @@ def lib() -> C.CDLL:
         L.oracle_render.restype = C.c_int
         L.oracle_render.argtypes = [C.POINTER(OracleFrame), C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                     C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(OracleStats)]
+        L.oracle_render_synth.restype = C.c_int
+        L.oracle_render_synth.argtypes = [C.POINTER(OracleFrame), C.c_uint32, C.c_uint32, C.c_double, C.c_double,
+                                          C.c_double, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                          C.POINTER(OracleStats)]
         L.oracle_synth_maps.restype = None
         L.oracle_synth_maps.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib = L
@@ -148,6 +151,20 @@ def render(frame: OracleFrame, heights: np.ndarray, colormap: np.ndarray, want_s
     r0, r1 = rows if rows is not None else (0, H)
     lib().oracle_render(C.byref(frame), heights.ctypes.data, colormap.ctypes.data, mw, mh,
                         framebuf.ctypes.data, steps.ctypes.data if want_steps else None, r0, r1, C.byref(st))
+    return framebuf, steps, st
+
+
+def render_synth(frame: OracleFrame, log2n: int, seed: int = 1234, lum=(0.299, 0.587, 0.114), rows=None,
+                 want_steps=True):
+    """oracle_render over the procedural synthetic map of size 2^log2n, texels generated on the fly (no arrays):
+    full-size parity bands for the BASELINE map sizes.  Returns (framebuf, step_index, stats); only `rows` are written."""
+    W, H = frame.screen_width, frame.screen_height
+    framebuf = np.zeros((H, W, 4), dtype=np.uint8)
+    steps = np.full((H, W), -3, dtype=np.int32) if want_steps else None
+    st = OracleStats()
+    r0, r1 = rows if rows is not None else (0, H)
+    lib().oracle_render_synth(C.byref(frame), log2n, seed, lum[0], lum[1], lum[2], framebuf.ctypes.data,
+                              steps.ctypes.data if want_steps else None, r0, r1, C.byref(st))
     return framebuf, steps, st
 
 

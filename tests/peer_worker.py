@@ -28,19 +28,25 @@ r.min_height, r.max_height = 0.0, 10.0
 r.synth_maps(10, 1234)
 stream = torch.cuda.Stream(device=0)
 torch.cuda.set_stream(stream)
-peer = MG.PeerFrame(r, H, W, rank, world, 0)
+completion = sys.argv[2] if len(sys.argv) > 2 else "device"
+channels = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+peer = MG.PeerFrame(r, H, W, rank, world, 0, channels=channels, completion=completion)
 ok = []
 for i, (proj, pos, vang) in enumerate([(1, (-3.0, 3.0, 14.0), 112.0), (2, (5.0, -5.0, 12.0), 120.0), (3, (-2.0, 2.0, 30.0), 125.0),
                                        (1, (12.0, 1.0, 11.0), 100.0)]):
     common = dict(projection=proj, screen_width=W, screen_height=H, cam_pos=pos, hang=hmrm.deg2rad(-45.0),
                   vang=hmrm.deg2rad(vang), hfov=hmrm.deg2rad(90.0), ortho_width=0.04, grid_width=0.01, step_dist=0.05)
-    r.render_device(r.frame(band_count=world, band_index=rank, **common), peer.pointer(i), stream.cuda_stream)
-    peer.complete()
+    fmt = hmrm.PIXEL_RGB8 if channels == 3 else hmrm.PIXEL_RGBA8
+    peer.render(r.frame(band_count=world, band_index=rank, pixel_format=fmt, **common), i, stream.cuda_stream)
+    peer.complete(i, stream.cuda_stream)
     if rank == 0:
-        got = peer.tensor(i).cpu().numpy()
+        got = peer.tensor(i).cpu().numpy()          # ordered after the completion on the current stream
         want = r.render(r.frame(**common))
-        ok.append(bool(np.array_equal(got, want)) and bool((got[..., 3] == 255).all()))
-    dist.barrier()          # nobody starts the next frame while rank 0 still reads this one (same buffer every 2 frames)
+        ok.append(bool(np.array_equal(got, want[..., :channels])) and (channels == 3 or bool((got[..., 3] == 255).all())))
+    peer.release(i, stream.cuda_stream)
+    if completion != "device":
+        dist.barrier()      # nobody starts the next frame while rank 0 still reads this one (same buffer every 2 frames)
+peer.check()
 peer.close()
 r.close()
 if rank == 0:

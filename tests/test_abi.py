@@ -35,7 +35,7 @@ def test_binding_prototypes_cover_header(hmrm):
 
 def test_abi_version_and_struct_sizes(hmrm):
     lib = hmrm.load_library()
-    assert lib.hmrm_abi_version() == 1
+    assert lib.hmrm_abi_version() == 2
     # struct layouts mirrored in ctypes must match the C compiler's (checked through defaults)
     f = hmrm.Frame()
     lib.hmrm_frame_defaults(C.byref(f))

@@ -44,4 +44,5 @@ def test_orbit_camera_stays_outside_the_box():
             x, y, z = c["pos"]
             inside = 0.0 <= x <= extent and -extent <= y <= 0.0 and bench.MIN_HEIGHT <= z <= bench.MAX_HEIGHT
             assert not inside, (name, n, c)
-            assert z > bench.MAX_HEIGHT
+            # (sample720 is the reference's own default camera: beside the map at z = 0, main/hmap.cpp:75)
+            assert z > bench.MAX_HEIGHT or wl.get("camera") == "sample"

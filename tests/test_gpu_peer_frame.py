@@ -16,8 +16,9 @@ pytestmark = pytest.mark.gpu
 HERE = Path(__file__).resolve().parent
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_bands_stored_into_the_root_frame_equal_the_whole_frame(hmrm, world, tmp_path):
+@pytest.mark.parametrize("world,completion,channels", [(2, "device", 4), (3, "device", 3), (2, "allreduce", 4),
+                                                       (3, "allreduce", 3)])
+def test_bands_stored_into_the_root_frame_equal_the_whole_frame(hmrm, world, completion, channels, tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -25,7 +26,7 @@ def test_bands_stored_into_the_root_frame_equal_the_whole_frame(hmrm, world, tmp
     procs = []
     for rank in range(world):
         env = dict(os.environ, RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
-        procs.append(subprocess.Popen([sys.executable, str(HERE / "peer_worker.py"), str(out)], env=env,
+        procs.append(subprocess.Popen([sys.executable, str(HERE / "peer_worker.py"), str(out), completion, str(channels)], env=env,
                                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     logs = []
     for p in procs:
