@@ -16,8 +16,11 @@ pytestmark = pytest.mark.gpu
 HERE = Path(__file__).resolve().parent
 
 
-@pytest.mark.parametrize("world,completion,channels", [(2, "device", 4), (3, "device", 3), (2, "allreduce", 4),
-                                                       (3, "allreduce", 3)])
+# completion = "allreduce" only: the device-side completion makes kernels of different ranks wait on one another, which
+# is only safe when every rank has its own GPU (several processes spinning on ONE GPU can hit a context-switch
+# timeout); its protocol is tested in one stream by test_device_side_completion_protocol_in_one_stream below and on
+# real GPUs by bench.py --gpus N (which asserts the gathered frame).
+@pytest.mark.parametrize("world,completion,channels", [(2, "allreduce", 4), (3, "allreduce", 3)])
 def test_bands_stored_into_the_root_frame_equal_the_whole_frame(hmrm, world, completion, channels, tmp_path):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -38,3 +41,44 @@ def test_bands_stored_into_the_root_frame_equal_the_whole_frame(hmrm, world, com
             raise
     assert all(p.returncode == 0 for p in procs), "\n".join(log[-1500:] for log in logs)
     assert json.loads(out.read_text()) == [True, True, True, True]
+
+
+def test_device_side_completion_protocol_in_one_stream(hmrm):
+    """hmrm_render_peer / hmrm_peer_wait / hmrm_peer_release (csrc/peer_sync.cuh) with three emulated ranks in ONE
+    process and ONE stream: every wait is already satisfied by kernels earlier in the stream, so nothing spins on
+    another launch.  Checks the counting (arrived = uses * ranks, released = uses), the frames (RGBA8 and RGB8, two
+    rotating buffers, six frames) and that no wait timed out."""
+    import numpy as np
+    import torch
+
+    from heightmap_ray_marcher_b200 import multi_gpu as MG
+
+    W, H, ranks = 322, 187, 3
+    r = hmrm.Renderer(0)
+    try:
+        r.min_height, r.max_height = 0.0, 10.0
+        r.synth_maps(10, 1234)
+        stream = torch.cuda.Stream(device=0)
+        torch.cuda.set_stream(stream)
+        for channels in (4, 3):
+            fmt = hmrm.PIXEL_RGB8 if channels == 3 else hmrm.PIXEL_RGBA8
+            pf = MG.PeerFrame(r, H, W, 0, 1, 0, channels=channels, completion="device")
+            for i in range(6):
+                common = dict(projection=1 + i % 3, screen_width=W, screen_height=H, cam_pos=(-3.0 + i, 3.0, 14.0 + i),
+                              hang=hmrm.deg2rad(-45.0), vang=hmrm.deg2rad(112.0), hfov=hmrm.deg2rad(90.0), ortho_width=0.04,
+                              grid_width=0.01, step_dist=0.05)
+                for rk in (2, 0, 1):         # any order: each call waits for the release of the previous use only
+                    r.render_peer(r.frame(band_count=ranks, band_index=rk, pixel_format=fmt, **common), pf.pointer(i),
+                                  pf.ctrl(i), pf.use(i), stream.cuda_stream)
+                r.peer_wait(pf.ctrl(i), pf.use(i), ranks, stream.cuda_stream)
+                got = pf.tensor(i).cpu().numpy()
+                r.peer_release(pf.ctrl(i), pf.use(i), stream.cuda_stream)
+                want = r.render(r.frame(**common))
+                assert np.array_equal(got, want[..., :channels]), (channels, i)
+            stream.synchronize()
+            for b in range(2):
+                assert r.peer_status(pf.ctrl(b)) == (3 * ranks, 3, 0)
+            pf.check()
+            pf.close()
+    finally:
+        r.close()
