@@ -123,7 +123,11 @@ _lib = None
 
 
 def library_path() -> Path:
-    return PKG / "libhmrm.so"
+    # HMRM_LIBRARY: another build of the SAME library (kernel experiments of tools/, e.g. variants/libhmrm_x.so)
+    import os
+
+    override = os.environ.get("HMRM_LIBRARY")
+    return Path(override) if override else PKG / "libhmrm.so"
 
 
 def load_library() -> C.CDLL:

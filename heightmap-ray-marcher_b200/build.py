@@ -66,6 +66,16 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> Path:
+    """Another build of the library with extra -D flags, for kernel A/B experiments (tools/): variants/libhmrm_<name>.so,
+    selected with HMRM_LIBRARY.  Never loaded by the product or the tests."""
+    out = PKG / "variants" / f"libhmrm_{name}.so"
+    out.parent.mkdir(exist_ok=True)
+    cmd = ["nvcc", *NVCC_FLAGS, *defines, "-o", str(out), *[str(s) for s in sources()]]
+    subprocess.run(cmd, check=True, cwd=str(PKG))
+    return out
+
+
 def build_hmap_fake_sdl(shim_dir: Path, fake_sdl_obj: Path, out: Path) -> Path:
     """Interactive `hmap` (-DHMAP_WITH_SDL) linked against a scripted fake SDL: test builds only (the shim and
     the object live with the test oracle; SDL2 itself is not installable in this image)."""

@@ -665,6 +665,10 @@ int hmrm_create(int device, hmrm_ctx **out) {
 		return fail(NULL, HMRM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
 		            prop.major, prop.minor);
 
+	if (const char *g = std::getenv("HMRM_L2_FETCH_GRANULARITY")) {
+		// experiment knob: bytes the L2 fetches from HBM per miss (32 / 64 / 128; a hint, device-wide)
+		cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)std::atoi(g));
+	}
 	hmrm_ctx *c = new hmrm_ctx();
 	c->device = device;
 	{

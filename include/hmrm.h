@@ -57,7 +57,7 @@ extern "C" {
 #define HMRM_LAYOUT_ROWMAJOR 0
 #define HMRM_LAYOUT_TILE4    1   /* 4x4-texel (32-byte sector) tiles, tiles in row-major order */
 #define HMRM_LAYOUT_ZORDER   2   /* 4x4-texel tiles in Z-order (Morton) inside 64x64-texel blocks */
-#define HMRM_LAYOUT_DEFAULT  HMRM_LAYOUT_TILE4
+#define HMRM_LAYOUT_DEFAULT  HMRM_LAYOUT_ROWMAJOR   /* measured: profiles/r02_layout_ab.txt — no layout wins */
 
 #define HMRM_OK                  0
 #define HMRM_ERR_INVALID         1   /* bad argument */

@@ -137,8 +137,9 @@ def test_pixel_format_switch_starts_from_a_cleared_framebuffer(hmrm, renderer, o
     sel = sel.reshape(part.shape[:2])
     assert not part[~sel].any() and np.array_equal(part[sel], H.golden_frames()["persp_basic"][..., :3][sel])
     bad = H.product_frame(hmrm, renderer, scene, pixel_format=9)
-    with pytest.raises(hmrm.HmrmError):
-        renderer.render(bad, out=np.zeros(part.shape, dtype=np.uint8))
+    with pytest.raises(hmrm.HmrmError) as e:
+        renderer.render(bad)
+    assert e.value.code == 1                                           # HMRM_ERR_INVALID
 
 
 # ---------------------------------------------------------------------------------------------------------------
