@@ -1,5 +1,5 @@
 // See image_io.hpp.  PNG / PNM / TGA decode to the pixel values stb_image v2.27 would return, PNG encode.
-#include "image_io.hpp"
+#include "image_internal.hpp"
 
 #include <zlib.h>
 
@@ -27,13 +27,7 @@ bool read_file(const std::string &path, std::vector<uint8_t> *data) {
 
 uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
 
-// ---------------------------------------------------------------------------------------------
-// Source image in "samples": src_channels per pixel (1 grey, 2 grey+alpha, 3 RGB, 4 RGBA), 8 bit.
-// ---------------------------------------------------------------------------------------------
-struct Decoded {
-	int w, h, channels;
-	std::vector<uint8_t> px;
-};
+} // namespace
 
 // stbi__convert_format semantics for 8-bit data
 void convert_channels(const Decoded &d, int want, Image *out) {
@@ -62,6 +56,8 @@ void convert_channels(const Decoded &d, int want, Image *out) {
 // ---------------------------------------------------------------------------------------------
 // PNG
 // ---------------------------------------------------------------------------------------------
+namespace {
+
 int paeth(int a, int b, int c) {
 	const int p = a + b - c;
 	const int pa = p > a ? p - a : a - p, pb = p > b ? p - b : b - p, pc = p > c ? p - c : c - p;
@@ -97,6 +93,8 @@ bool unfilter(uint8_t *raw, int rows, size_t stride, int bpp, std::string *error
 	}
 	return true;
 }
+
+} // namespace
 
 bool decode_png(const std::vector<uint8_t> &file, Decoded *out, std::string *error) {
 	static const uint8_t sig[8] = {137, 80, 78, 71, 13, 10, 26, 10};
@@ -257,113 +255,35 @@ bool decode_png(const std::vector<uint8_t> &file, Decoded *out, std::string *err
 
 // ---------------------------------------------------------------------------------------------
 // binary PNM (P5 / P6, maxval <= 255; samples are taken as they are, like stb_image)
-// ---------------------------------------------------------------------------------------------
-bool decode_pnm(const std::vector<uint8_t> &file, Decoded *out, std::string *error) {
-	size_t pos = 2;
-	int vals[3], got = 0;
-	while (got < 3 && pos < file.size()) {
-		const uint8_t c = file[pos];
-		if (c == '#') {
-			while (pos < file.size() && file[pos] != '\n' && file[pos] != '\r') ++pos;
-		}
-		else if (c == ' ' || c == '\t' || c == '\n' || c == '\v' || c == '\f' || c == '\r') ++pos;
-		else if (c >= '0' && c <= '9') {
-			long v = 0;
-			while (pos < file.size() && file[pos] >= '0' && file[pos] <= '9') {
-				v = v * 10 + (file[pos] - '0');
-				if (v > (1 << 30)) { *error = "PNM header value too large"; return false; }
-				++pos;
-			}
-			vals[got++] = (int)v;
-		}
-		else { *error = "bad PNM header"; return false; }
-	}
-	if (got < 3 || pos >= file.size()) { *error = "truncated PNM header"; return false; }
-	++pos;   // the single whitespace byte after maxval
-	if (vals[2] > 255) { *error = "16-bit PNM is not supported"; return false; }
-	out->w = vals[0];
-	out->h = vals[1];
-	out->channels = file[1] == '6' ? 3 : 1;
-	const size_t need = (size_t)out->w * (size_t)out->h * (size_t)out->channels;
-	if (out->w <= 0 || out->h <= 0 || file.size() - pos < need) { *error = "truncated PNM data"; return false; }
-	out->px.assign(file.begin() + (long)pos, file.begin() + (long)(pos + need));
-	return true;
-}
-
-// ---------------------------------------------------------------------------------------------
-// TGA: true-colour 24/32 bit and 8-bit grey, raw or RLE, either vertical origin
-// ---------------------------------------------------------------------------------------------
-bool decode_tga(const std::vector<uint8_t> &file, Decoded *out, std::string *error) {
-	if (file.size() < 18) { *error = "truncated TGA"; return false; }
-	const int id_len = file[0], cmap_type = file[1], type = file[2];
-	const int w = file[12] | (file[13] << 8), h = file[14] | (file[15] << 8), bpp = file[16], desc = file[17];
-	const bool rle = type == 10 || type == 11;
-	const int base = rle ? type - 8 : type;
-	if (cmap_type != 0 || (base != 2 && base != 3)) { *error = "unsupported TGA type (palette / 16-bit)"; return false; }
-	if (!((base == 2 && (bpp == 24 || bpp == 32)) || (base == 3 && bpp == 8))) { *error = "unsupported TGA depth"; return false; }
-	if (w <= 0 || h <= 0) { *error = "bad TGA size"; return false; }
-	const int n = bpp / 8;
-	out->w = w;
-	out->h = h;
-	out->channels = n;
-	out->px.resize((size_t)w * h * (size_t)n);
-	size_t pos = 18 + (size_t)id_len;
-	const size_t npx = (size_t)w * h;
-	uint8_t pixel[4] = {0, 0, 0, 0};
-	size_t i = 0;
-	int run = 0;
-	bool run_is_rle = false;
-	while (i < npx) {
-		bool fetch = true;
-		if (rle) {
-			if (run == 0) {
-				if (pos >= file.size()) { *error = "truncated TGA data"; return false; }
-				const int c = file[pos++];
-				run = 1 + (c & 127);
-				run_is_rle = (c & 128) != 0;
-			}
-			else if (run_is_rle) fetch = false;
-		}
-		if (fetch) {
-			if (pos + (size_t)n > file.size()) { *error = "truncated TGA data"; return false; }
-			std::memcpy(pixel, &file[pos], (size_t)n);
-			pos += (size_t)n;
-		}
-		const size_t y = i / (size_t)w, x = i % (size_t)w;
-		const size_t oy = (desc & 0x20) ? y : (size_t)h - 1 - y;      // bit 5: top-left origin
-		uint8_t *t = &out->px[(oy * w + x) * (size_t)n];
-		if (n >= 3) { t[0] = pixel[2]; t[1] = pixel[1]; t[2] = pixel[0]; if (n == 4) t[3] = pixel[3]; }   // BGR(A) on disk
-		else t[0] = pixel[0];
-		++i;
-		if (rle) --run;
-	}
-	return true;
-}
-
-bool ends_with(const std::string &s, const char *suffix) {
-	const size_t n = std::strlen(suffix);
-	if (s.size() < n) return false;
-	for (size_t i = 0; i < n; ++i) {
-		char a = s[s.size() - n + i], b = suffix[i];
-		if (a >= 'A' && a <= 'Z') a = (char)(a - 'A' + 'a');
-		if (a != b) return false;
-	}
-	return true;
-}
-
-} // namespace
-
 bool load_image(const std::string &path, int want_channels, Image *out, std::string *error) {
 	std::vector<uint8_t> file;
 	std::string err;
 	if (want_channels != 3 && want_channels != 4) { *error = "want_channels must be 3 or 4"; return false; }
 	if (!read_file(path, &file)) { *error = "cannot read file"; return false; }
+	// Format by content, in the order stb tries its loaders (vendor/stb_image.h stbi__load_main :1118-1170):
+	// PNG, BMP, GIF, PSD, PIC, JPEG, PNM, HDR, and TGA last because it has no signature.
 	Decoded d;
 	bool ok;
-	if (file.size() >= 8 && file[0] == 137 && file[1] == 'P' && file[2] == 'N' && file[3] == 'G') ok = decode_png(file, &d, &err);
-	else if (file.size() >= 2 && file[0] == 'P' && (file[1] == '5' || file[1] == '6')) ok = decode_pnm(file, &d, &err);
-	else if (ends_with(path, ".tga")) ok = decode_tga(file, &d, &err);
-	else { ok = false; err = "unsupported image format (PNG, binary PGM/PPM and TGA are supported)"; }
+	const size_t n = file.size();
+	if (n >= 8 && file[0] == 137 && file[1] == 'P' && file[2] == 'N' && file[3] == 'G') ok = decode_png(file, &d, &err);
+	else if (looks_like_bmp(file)) ok = decode_bmp(file, &d, &err);
+	else if (n >= 6 && !std::memcmp(file.data(), "GIF8", 4) && (file[4] == '7' || file[4] == '9') && file[5] == 'a') ok = decode_gif(file, &d, &err);
+	else if (n >= 4 && !std::memcmp(file.data(), "8BPS", 4)) ok = decode_psd(file, &d, &err);
+	else if (n >= 92 && !std::memcmp(file.data(), "\x53\x80\xF6\x34", 4) && !std::memcmp(file.data() + 88, "PICT", 4)) {
+		ok = false;
+		err = "Softimage PIC is not supported";
+	}
+	else if (n >= 2 && file[0] == 0xFF && file[1] == 0xD8) {
+		if (!decode_jpeg(file, want_channels, out, &err)) { *error = err; return false; }
+		return true;
+	}
+	else if (n >= 2 && file[0] == 'P' && (file[1] == '5' || file[1] == '6')) ok = decode_pnm(file, want_channels, &d, &err);
+	else if ((n >= 10 && !std::memcmp(file.data(), "#?RADIANCE", 10)) || (n >= 6 && !std::memcmp(file.data(), "#?RGBE", 6))) {
+		ok = false;
+		err = "Radiance HDR is not supported";
+	}
+	else if (looks_like_tga(file)) ok = decode_tga(file, &d, &err);
+	else { ok = false; err = "unknown image type"; }
 	if (!ok) { *error = err; return false; }
 	convert_channels(d, want_channels, out);
 	return true;

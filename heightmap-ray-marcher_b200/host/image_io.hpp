@@ -4,10 +4,17 @@
 //   heightmap: stbi_load(path, &w, &h, &n, 3)  -> RGB8   (main/hmap.cpp:320-321)
 //   colormap : stbi_load(path, &w, &h, &n, 4)  -> RGBA8  (main/hmap.cpp:341-342)
 // and writes frames with stbi_write_png(path, w, h, 4, buf, w*4) (main/hmap.cpp:158-160).
-// This is an independent implementation of the same *decoded-pixel contract* for the formats
-// that have an exact one: PNG (all colour types and bit depths, tRNS, Adam7), binary PNM
-// (P5/P6, 8 and 16 bit) and uncompressed / RLE true-colour and grey TGA.  JPEG & co. would need
-// IDCT-exact parity and are rejected.
+// This is an independent implementation of the same *decoded-pixel contract* — for every file the pixels stb returns,
+// byte for byte (tests/golden/images.json holds stb's own output for each flavour):
+//   PNG   all colour types and bit depths, tRNS, Adam7                                   image_io.cpp
+//   JPEG  baseline and progressive, 1 / 3 / 4 components, any subsampling, restarts      image_jpeg.cpp
+//   BMP   1/4/8-bit palette, 16/24/32-bit with bit fields, OS/2 and V4/V5 headers         image_formats.cpp
+//   GIF   first frame (interlace, transparency, local colour table, background fill)      image_formats.cpp
+//   PSD   composited RGB(A), 8/16 bit, raw or RLE                                          image_formats.cpp
+//   TGA   true colour 15/16/24/32, grey, grey+alpha, colour-mapped, raw or RLE            image_formats.cpp
+//   PNM   binary P5 / P6, 8 bit, and 16 bit where stb's result is defined                 image_formats.cpp
+// The format is recognised from the file's content in stb's order (TGA last: it has no signature), not from its name.
+// Not supported (stb_image reads them): Radiance HDR and Softimage PIC; BMP RLE is refused by stb too.
 //
 // Conversion rules reproduced (vendor/stb_image.h: stbi__convert_format, stbi__convert_16_to_8,
 // stbi__compute_transparency, stbi__expand_png_palette): grey -> R=G=B; missing alpha -> 255;

@@ -60,6 +60,8 @@ def make_images():
         f.write(b"P5\n# a comment\n%d %d\n255\n" % (w, h))
         f.write(grey.tobytes())
     O.write_tga_rgba(IMAGES / "rgba.tga", rgba)
+    # every other format stb_image reads for the reference: JPEG, BMP, GIF, TGA flavours, PSD, 16-bit PNM
+    subprocess.run([sys.executable, str(HERE / "gen_format_images.py"), str(IMAGES)], check=True)
 
 
 def write_png_raw(path, arr, depth, color, interlace=False):
@@ -131,6 +133,9 @@ CONFIGS = {
     "unreadable_heightmap": "hfov 60 heightmap does_not_exist.png colormap rgba8.png\n",
     "size_conflict": "heightmap grey8.png colormap other_size.png\n",
     "pnm_tga": "heightmap grey.pgm colormap rgba.tga resolution 32 18 cycle 1\n",
+    # the reference's own sample_config.txt names JPEG maps ("heightmap path/to/img.jpg")
+    "jpeg_maps": "heightmap grey.jpg colormap base_444.jpg resolution 32 18\n",
+    "bmp_gif_maps": "heightmap rgb24.bmp colormap transparent.gif\n",
 }
 
 

@@ -39,6 +39,12 @@ def test_config_grammar_echo_matches_reference(hmap, name, tmp_path):
 IMG = json.loads((GOLDEN / "images.json").read_text())
 
 
+# stb_image 2.27 narrows a 16-bit PNM whose channel count must change by running its 8-bit converter over the 16-bit
+# buffer and then reading past its end (vendor/stb_image.h:7449-7453, :1202-1206): those pixels are undefined and
+# the recorded hash is one run's heap contents.  Ours refuses such a file instead.
+STB_UNDEFINED = {("rgb16.ppm", 4)}
+
+
 @pytest.mark.parametrize("name", sorted(IMG))
 @pytest.mark.parametrize("comp", [3, 4])
 def test_image_decode_matches_stb(hmap, name, comp, tmp_path):
@@ -46,6 +52,9 @@ def test_image_decode_matches_stb(hmap, name, comp, tmp_path):
     out = tmp_path / "o.raw"
     res = subprocess.run([str(hmap), "--decode-image", str(IMAGES / name), str(comp), str(out)], capture_output=True,
                          text=True)
+    if (name, comp) in STB_UNDEFINED:
+        assert res.returncode == 1 and "out of bounds" in res.stderr
+        return
     assert want is not None and res.returncode == 0, res.stderr
     w, h, c = (int(v) for v in res.stdout.split())
     assert (w, h, c) == (want["width"], want["height"], comp)
