@@ -397,15 +397,17 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
     E2E_DEPTH = 3                               # frames that may stay in flight behind the newest one
     host_bufs = [binding.pinned_empty((H, W, job.channels)) for _ in range(E2E_DEPTH + 1)]
 
-    # bands at N > 1: ONE host frame in POSIX shared memory, page-locked by every rank; each rank copies its own tile
-    # rows out over its own PCIe link (hmrm_render_async with band_count > 1), a barrier completes the frame
+    # bands at N > 1: the host frames live in POSIX shared memory, page-locked by every rank; each rank copies its own
+    # tile rows out over its own PCIe link (hmrm_render_async with band_count > 1).  Two frames rotate: while frame i is
+    # rendered and copied, the ranks agree (all-reduce, host-synchronised) that frame i - 1 is complete in host memory.
     shared = shared_np = None
     if bands and world > 1:
         from multiprocessing import shared_memory
 
+        frame_bytes = H * W * job.channels
         name = [None]
         if rank == 0:
-            shared = shared_memory.SharedMemory(create=True, size=H * W * job.channels)
+            shared = shared_memory.SharedMemory(create=True, size=2 * frame_bytes)
             name[0] = shared.name
         dist.broadcast_object_list(name, src=0)
         if rank != 0:
@@ -413,31 +415,40 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
             from multiprocessing import resource_tracker
 
             resource_tracker.unregister(shared._name, "shared_memory")     # rank 0 owns (and unlinks) the segment
-        shared_np = np.ndarray((H, W, job.channels), dtype=np.uint8, buffer=shared.buf)
-        if binding.load_library().hmrm_host_register(shared_np.ctypes.data, H * W * job.channels) != 0:
+        shared_np = np.ndarray((2, H, W, job.channels), dtype=np.uint8, buffer=shared.buf)
+        if binding.load_library().hmrm_host_register(shared_np.ctypes.data, 2 * frame_bytes) != 0:
             raise SystemExit("hmrm_host_register failed")
         e2e_token = torch.zeros(1, device=f"cuda:{local}")
 
+    def frame_complete_everywhere() -> None:
+        dist.all_reduce(e2e_token)
+        e2e_token.cpu()                        # host-synchronised: every rank's copy of that frame has landed
+
     def e2e_step(i: int, n: int) -> None:
         if bands and world > 1:
-            r.render_async(job.frame_of(n), shared_np)
-            r.wait()
-            dist.all_reduce(e2e_token)         # the frame is complete in host memory once every rank's copy is
-            torch.cuda.synchronize()
+            r.render_async(job.frame_of(n), shared_np[i % 2])
+            r.wait_pending(1)                  # this rank's part of frame i - 1 is in host memory
+            if i > 0:
+                frame_complete_everywhere()    # ... and everybody else's: frame i - 1 is whole
         else:
             # the library's streaming call: the newest frames render while an older one is still being copied to the
             # host; after wait_pending(d) frame i-d is complete in its host buffer (d + 1 buffers rotate)
             r.render_async(job.frame_of(n, whole=True), host_bufs[i % (E2E_DEPTH + 1)])
             r.wait_pending(E2E_DEPTH)
 
+    def e2e_drain() -> None:
+        r.wait()
+        if bands and world > 1:
+            frame_complete_everywhere()
+
     for i, n in enumerate(warm_frames):
         e2e_step(i, n)
-    r.wait()
+    e2e_drain()
     barrier()
     t0 = time.perf_counter()
     for i, n in enumerate(my_frames):
         e2e_step(i, n)
-    r.wait()
+    e2e_drain()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     barrier()
@@ -573,8 +584,9 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms / steps,
                     "h2d_bytes_per_step": 1024, "d2h_bytes_per_step": W * H * job.channels,
                     "d2h_gbs": W * H * job.channels * frames_total / (e2e_ms * 1e-3) / 1e9,
-                    "api": ("hmrm_render_async with band_count = N into ONE host frame in shared memory, page-locked by every "
-                            "rank: each rank copies its own tile rows out over its own PCIe link; all-reduce as the barrier")
+                    "api": ("hmrm_render_async with band_count = N into a host frame in shared memory, page-locked by every "
+                            "rank: each rank copies its own tile rows out over its own PCIe link; two host frames rotate and "
+                            "an all-reduce per frame tells every rank that the previous frame is whole")
                     if (bands and world > 1) else "hmrm_render_async + hmrm_wait_pending(3): every frame lands in pinned host memory; the "
                            "copy-out of frame n overlaps the kernels of the next frames (four device + four host "
                            "buffers)"},
@@ -606,7 +618,7 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
         ok_host = True
         if rank == 0:
             # the host frame of the last e2e step must be the frame itself
-            ok_host = bool(np.array_equal(shared_np, r.render(job.frame_of(my_frames[-1], whole=True))))
+            ok_host = bool(np.array_equal(shared_np[(len(my_frames) - 1) % 2], r.render(job.frame_of(my_frames[-1], whole=True))))
         binding.load_library().hmrm_host_unregister(shared_np.ctypes.data)
         del shared_np
         dist.barrier()

@@ -352,6 +352,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	P.cycle = f->cycle;
 	P.period = f->cycle_period;
 	P.tiles_x = (W + 7) / 8;
+	P.inv_tiles_x = std::nextafterf(1.0f / (float)P.tiles_x, 0.0f) * (1.0f - 1.0e-6f);
 	const int tile_rows = (row_end - row_begin + 3) / 4;
 	if (f->band_count > 1) {
 		// interleaved bands: sky rows are almost free and terrain rows are not, so contiguous bands balance badly
@@ -380,6 +381,10 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	P.c1[0] = P.c0[0] + c->map_w * f->grid_width;
 	P.c1[1] = P.c0[1] - c->map_h * f->grid_width;
 	P.c1[2] = c->max_height;
+	for (int i = 0; i < 3; ++i) {
+		P.bmin[i] = std::fmin(P.c0[i], P.c1[i]);
+		P.bmax[i] = std::fmax(P.c0[i], P.c1[i]);
+	}
 	P.gw = f->grid_width;
 	P.nudge = f->grid_width * 0.01;
 	P.step_dist = f->step_dist;
@@ -862,10 +867,10 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 	q.min_height = min_height;
 	q.span = max_height - min_height;
 	const long long n = (long long)c->map_w * c->map_h;
-	// (1) range of surf from a sample of the rows (at most ~8 M cells): only the quantiser's resolution depends on it
+	// (1) range of surf from a sample of the rows (at most ~1 M cells): only the quantiser's resolution depends on it
 	const unsigned long long init_bits[3] = {0ULL, ~0ULL, 0ULL};
 	HMRM_CUDA(c, cudaMemcpyAsync(c->d_max_bits, init_bits, sizeof init_bits, cudaMemcpyHostToDevice, c->stream));
-	int row_stride = (int)((n + (8LL << 20) - 1) / (8LL << 20));
+	int row_stride = (int)((n + (1LL << 20) - 1) / (1LL << 20));
 	if (row_stride < 1) row_stride = 1;
 	k1_range<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_rgb, c->map_w, c->map_h, row_stride, q, c->d_max_bits,
 	                                                 c->d_max_bits + 1);
@@ -938,7 +943,7 @@ int hmrm_update_heightmap(hmrm_ctx *c, const double lum[3], double min_height, d
 			job.dst_pitch[l] = pyr_level_pitch(c->layout, c->mip_w[l]);
 			if (l >= 1) {
 				job.first_item[l] = items;
-				items += (unsigned long long)((c->mip_w[l] + 3) / 4) * (unsigned long long)c->mip_h[l];
+				items += (unsigned long long)((c->mip_w[l] + 3) / 4) * (unsigned long long)((c->mip_h[l] + 3) / 4);
 			}
 			job.first_item[l + 1] = items;
 		}

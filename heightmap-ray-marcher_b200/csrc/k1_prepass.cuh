@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(256) k1_mip_upper(uint16_t *__restrict__ plain
 //
 // dst(l)[y][x] = max of plain(l) over the 3x3 neighbourhood (clipped): a sample that clears dst clears the block it
 // is in AND the eight blocks around it, so a jump may run on into the neighbouring blocks instead of stopping at an
-// edge.  Work item = four horizontally adjacent outputs (x multiple of 4): in the tiled layouts those are contiguous.
+// edge.
 struct DilateJob {
 	int n_levels;
 	int layout;
@@ -358,51 +358,74 @@ struct DilateJob {
 };
 
 __global__ void __launch_bounds__(256) k1_dilate_levels(const uint16_t *__restrict__ plain, uint16_t *__restrict__ pyr, DilateJob job) {
+	// Work item = a 4 x 4 block of outputs: six input rows (two of halo), each one 8-byte load plus its two horizontal
+	// neighbours, give the sixteen 3x3 maxima; in the tiled layouts the block is one 32-byte sector of the destination.
 	const unsigned long long total = job.first_item[job.n_levels];
 	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
 	for (unsigned long long item = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
 		int l = 1;
 		while (l + 1 < job.n_levels && item >= job.first_item[l + 1]) l += 1;
-		const int w = job.w[l], h = job.h[l], wq = (w + 3) / 4;
-		const unsigned long long t = item - job.first_item[l];
-		const int xq = (int)(t % (unsigned)wq), y = (int)(t / (unsigned)wq);
-		const int x = xq * 4;
+		const int w = job.w[l], h = job.h[l];
+		const unsigned wq = (unsigned)(w + 3) / 4u;
+		const unsigned t = (unsigned)(item - job.first_item[l]);          // < 2^26 items per level
+		const int xq = (int)(t % wq), yq = (int)(t / wq);
+		const int x = xq * 4, y = yq * 4;
 		const uint16_t *src = plain + job.plain_off[l];
-		unsigned o0 = 0, o1 = 0, o2 = 0, o3 = 0;
 		const bool vec = (w & 3) == 0;
-		for (int dy = -1; dy <= 1; ++dy) {
-			const int yy = y + dy;
-			if (yy < 0 || yy >= h) continue;
-			const uint16_t *row = src + (size_t)yy * w;
-			unsigned c0, c1, c2, c3;
-			if (vec) {
-				const uint2 v = __ldg((const uint2 *)(row + x));
-				c0 = v.x & 0xFFFFu; c1 = v.x >> 16; c2 = v.y & 0xFFFFu; c3 = v.y >> 16;
+		unsigned hmax[6][4];           // per input row y-1 .. y+4: horizontal 3-max of the four columns
+#pragma unroll
+		for (int r = 0; r < 6; ++r) {
+			const int yy = y - 1 + r;
+			unsigned c0 = 0u, c1 = 0u, c2 = 0u, c3 = 0u, lft = 0u, rgt = 0u;
+			if (yy >= 0 && yy < h) {
+				const uint16_t *row = src + (size_t)yy * w;
+				if (vec) {
+					const uint2 v = __ldg((const uint2 *)(row + x));
+					c0 = v.x & 0xFFFFu; c1 = v.x >> 16; c2 = v.y & 0xFFFFu; c3 = v.y >> 16;
+				}
+				else {
+					c0 = __ldg(row + x);
+					if (x + 1 < w) c1 = __ldg(row + x + 1);
+					if (x + 2 < w) c2 = __ldg(row + x + 2);
+					if (x + 3 < w) c3 = __ldg(row + x + 3);
+				}
+				if (x > 0) lft = __ldg(row + x - 1);
+				if (x + 4 < w) rgt = __ldg(row + x + 4);
 			}
-			else {
-				c0 = __ldg(row + x);
-				c1 = x + 1 < w ? (unsigned)__ldg(row + x + 1) : 0u;
-				c2 = x + 2 < w ? (unsigned)__ldg(row + x + 2) : 0u;
-				c3 = x + 3 < w ? (unsigned)__ldg(row + x + 3) : 0u;
-			}
-			const unsigned lft = x > 0 ? (unsigned)__ldg(row + x - 1) : 0u;
-			const unsigned rgt = x + 4 < w ? (unsigned)__ldg(row + x + 4) : 0u;
-			o0 = max(o0, max(lft, max(c0, c1)));
-			o1 = max(o1, max(c0, max(c1, c2)));
-			o2 = max(o2, max(c1, max(c2, c3)));
-			o3 = max(o3, max(c2, max(c3, rgt)));
+			hmax[r][0] = max(lft, max(c0, c1));
+			hmax[r][1] = max(c0, max(c1, c2));
+			hmax[r][2] = max(c1, max(c2, c3));
+			hmax[r][3] = max(c2, max(c3, rgt));
 		}
 		uint16_t *dst = pyr + job.dst_off[l];
-		const unsigned at = pyr_index_rt(job.layout, (unsigned)x, (unsigned)y, job.dst_pitch[l]);
-		if (vec || job.layout != kLayoutRowMajor) {
-			// row-major with w % 4 == 0, or a tiled layout (rows of a sector are 4 texels, padded): one 8-byte store
-			*(uint2 *)(dst + at) = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+		uint2 rows[4];
+#pragma unroll
+		for (int r = 0; r < 4; ++r) {
+			const unsigned o0 = max(hmax[r][0], max(hmax[r + 1][0], hmax[r + 2][0]));
+			const unsigned o1 = max(hmax[r][1], max(hmax[r + 1][1], hmax[r + 2][1]));
+			const unsigned o2 = max(hmax[r][2], max(hmax[r + 1][2], hmax[r + 2][2]));
+			const unsigned o3 = max(hmax[r][3], max(hmax[r + 1][3], hmax[r + 2][3]));
+			rows[r] = make_uint2(o0 | (o1 << 16), o2 | (o3 << 16));
+		}
+		if (job.layout != kLayoutRowMajor) {
+			// one sector: rows of the block are consecutive (the level's allocation is padded to whole sectors)
+			uint4 *sp = (uint4 *)(dst + pyr_index_rt(job.layout, (unsigned)x, (unsigned)y, job.dst_pitch[l]));
+			sp[0] = make_uint4(rows[0].x, rows[0].y, rows[1].x, rows[1].y);
+			sp[1] = make_uint4(rows[2].x, rows[2].y, rows[3].x, rows[3].y);
 		}
 		else {
-			dst[at] = (uint16_t)o0;
-			if (x + 1 < w) dst[at + 1] = (uint16_t)o1;
-			if (x + 2 < w) dst[at + 2] = (uint16_t)o2;
-			if (x + 3 < w) dst[at + 3] = (uint16_t)o3;
+#pragma unroll
+			for (int r = 0; r < 4; ++r) {
+				if (y + r >= h) break;
+				uint16_t *d = dst + (size_t)(y + r) * w + x;
+				if (vec) *(uint2 *)d = rows[r];
+				else {
+					d[0] = (uint16_t)(rows[r].x & 0xFFFFu);
+					if (x + 1 < w) d[1] = (uint16_t)(rows[r].x >> 16);
+					if (x + 2 < w) d[2] = (uint16_t)(rows[r].y & 0xFFFFu);
+					if (x + 3 < w) d[3] = (uint16_t)(rows[r].y >> 16);
+				}
+			}
 		}
 	}
 }

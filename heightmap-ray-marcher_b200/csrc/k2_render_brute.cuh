@@ -23,6 +23,20 @@ __device__ __forceinline__ unsigned next_tile(unsigned int *counter) {
 	return __shfl_sync(0xFFFFFFFFu, t, 0);
 }
 
+// tile -> (row, column) of the launch's tile grid.  The float estimate of the quotient never exceeds it (reciprocal
+// and conversions round down; tile < 2^26 so the conversion is exact below 2^24 and off by < 4 above, where
+// tiles_x >= 1024), and is short by at most a couple of units: fixed up with compares instead of an integer divide.
+__device__ __forceinline__ void tile_row_col(const RenderParams &P, unsigned tile, int &row, int &col) {
+	unsigned q = __float2uint_rz(__uint2float_rz(tile) * P.inv_tiles_x);
+	unsigned r = tile - q * (unsigned)P.tiles_x;
+	while (r >= (unsigned)P.tiles_x) {
+		r -= (unsigned)P.tiles_x;
+		q += 1u;
+	}
+	row = (int)q;
+	col = (int)r;
+}
+
 // Does pixel (px,py) belong to this frame?  (cycle interleave main/hmap.cpp:979-981, row band)
 __device__ __forceinline__ bool pixel_selected(const RenderParams &P, int px, int py) {
 	if (px >= P.W || py >= P.row_end) return false;
@@ -79,8 +93,8 @@ __global__ void __launch_bounds__(256) k2_render_brute(const __grid_constant__ R
 	for (;;) {
 		const unsigned tile = next_tile(P.tile_counter);
 		if (tile >= n_tiles) break;
-		const int ty = (int)(tile / (unsigned)P.tiles_x);
-		const int tx = (int)(tile - (unsigned)ty * (unsigned)P.tiles_x);
+		int ty, tx;
+		tile_row_col(P, tile, ty, tx);
 		const int px = tx * 8 + (lane & 7);
 		const int py = P.row_begin + (P.tile_y_first + ty * P.tile_y_step) * 4 + (lane >> 3);
 		const bool active = pixel_selected(P, px, py);

@@ -455,8 +455,8 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin
 			if (cur >= n_tiles) break;
 		}
 		const unsigned tile = cur++;
-		const int ty_seq = (int)(tile / (unsigned)P.tiles_x);
-		const int tx = (int)(tile - (unsigned)ty_seq * (unsigned)P.tiles_x);
+		int ty_seq, tx;
+		tile_row_col(P, tile, ty_seq, tx);
 		// longest-processing-time-first: a few grazing tiles take ~50x the mean, so they must start early
 		const int ty = P.row_order ? __ldg(P.row_order + HMRM_CHECKED(P, ty_seq, P.tiles_y)) : ty_seq;
 		const int px = tx * 8 + (lane & 7);

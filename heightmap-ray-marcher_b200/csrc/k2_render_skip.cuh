@@ -323,8 +323,8 @@ __global__ void __launch_bounds__(256, 4) k2_render_skip(const __grid_constant__
 	for (;;) {
 		const unsigned tile = next_tile(P.tile_counter);
 		if (tile >= n_tiles) break;
-		const int ty_seq = (int)(tile / (unsigned)P.tiles_x);
-		const int tx = (int)(tile - (unsigned)ty_seq * (unsigned)P.tiles_x);
+		int ty_seq, tx;
+		tile_row_col(P, tile, ty_seq, tx);
 		// longest-processing-time-first: a few grazing tiles take ~50x the mean, so they must start early
 		const int ty = P.row_order ? __ldg(P.row_order + HMRM_CHECKED(P, ty_seq, P.tiles_y)) : ty_seq;
 		const int px = tx * 8 + (lane & 7);

@@ -43,7 +43,7 @@ __device__ __forceinline__ Ray generate_ray(const RenderParams &P, int px, int p
 		const double vz = fsub(qz, P.cam[2]);
 		// glm::normalize: v * (1 / sqrt(dot(v, v))), dot = (x*x + y*y) + z*z
 		const double len2 = fadd(fadd(fmul(vx, vx), fmul(vy, vy)), fmul(vz, vz));
-		const double inv = fdiv(1.0, fsqrt(len2));
+		const double inv = frcp(fsqrt(len2));
 		r.ox = P.cam[0]; r.oy = P.cam[1]; r.oz = P.cam[2];
 		r.dx = fmul(vx, inv);
 		r.dy = fmul(vy, inv);
@@ -91,7 +91,24 @@ __device__ __forceinline__ bool box_entry_at(const double *c0, const double *c1,
 	return true;
 }
 
+// A ray that starts outside one slab of the box and points away from it on that axis cannot enter: both of that
+// axis' quotients (c - o) / d are then strictly negative (never NaN: numerator and denominator are non-zero), so
+// distance() either bails out with +inf or returns lo <= hi < 0 and intersection() rejects d < 0 (src/AABB.cpp:36-39,
+// :69-76).  Decided exactly, without the six divides — every ray above the horizon of a camera above the terrain.
+__device__ __forceinline__ bool certain_miss(const RenderParams &P, const Ray &r) {
+	return (r.ox > P.bmax[0] && r.dx > 0.0) || (r.ox < P.bmin[0] && r.dx < 0.0) ||
+	       (r.oy > P.bmax[1] && r.dy > 0.0) || (r.oy < P.bmin[1] && r.dy < 0.0) ||
+	       (r.oz > P.bmax[2] && r.dz > 0.0) || (r.oz < P.bmin[2] && r.dz < 0.0);
+}
+
+// `dist` is only meaningful when the slab test ran (always when P.ray_dump is set).
 __device__ __forceinline__ bool box_entry(const RenderParams &P, const Ray &r, double &ex, double &ey, double &ez, double &dist) {
+#ifndef HMRM_EXP_NO_EARLYOUT
+	if (!P.ray_dump && certain_miss(P, r)) {
+		dist = __longlong_as_double(0x7FF0000000000000LL);
+		return false;
+	}
+#endif
 	return box_entry_at(P.c0, P.c1, r, ex, ey, ez, dist);
 }
 

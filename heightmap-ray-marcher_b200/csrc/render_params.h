@@ -27,6 +27,7 @@ struct RenderParams {
 	int row_begin, row_end;
 	int cycle, period;
 	int tiles_x, tiles_y;          // 8x4-pixel tiles this launch renders
+	float inv_tiles_x;             // slightly less than 1 / tiles_x: tile -> (row, column) without an integer divide
 	int tile_y_first, tile_y_step; // launch tile row t is frame tile row tile_y_first + t * tile_y_step (row interleave)
 	const int *row_order;          // optional permutation of the launch tile rows: expensive (grazing) rows first
 	unsigned batch_from_tile;      // tiles from this queue position on look above the horizon: grabbed 8 at a time
@@ -42,6 +43,7 @@ struct RenderParams {
 	double cam[3], ul[3], pr[3], pd[3], look[3];
 	// AABB (main/hmap.cpp:967-974) and march constants
 	double c0[3], c1[3];
+	double bmin[3], bmax[3];       // the same box as per-axis min / max (c1.y is negative: main/hmap.cpp:971)
 	double gw;                     // grid_width
 	double nudge;                  // fl(grid_width * 0.01), :998
 	double step_dist;
