@@ -27,6 +27,7 @@ from .binding import (  # noqa: F401
     SPHERICAL,
     TRAVERSAL_AUTO,
     TRAVERSAL_BRUTE,
+    TRAVERSAL_PACK,
     TRAVERSAL_SKIP,
     TRAVERSAL_SKIP_FP64,
     Frame,
@@ -43,6 +44,6 @@ from .binding import (  # noqa: F401
 __all__ = [
     "Renderer", "Frame", "Stats", "HmrmError", "load_library", "library_path", "deg2rad", "camera_basis",
     "get_ray", "PERSPECTIVE", "SPHERICAL", "ORTHOGRAPHIC", "FP64_EXACT", "FP32_FAST", "TRAVERSAL_AUTO",
-    "TRAVERSAL_BRUTE", "TRAVERSAL_SKIP", "FLAG_STATS", "FLAG_STEP_INDEX", "FLAG_RAY_DUMP", "PIXEL_RGBA8", "PIXEL_RGB8",
+    "TRAVERSAL_BRUTE", "TRAVERSAL_SKIP", "TRAVERSAL_PACK", "FLAG_STATS", "FLAG_STEP_INDEX", "FLAG_RAY_DUMP", "PIXEL_RGBA8", "PIXEL_RGB8",
     "LAYOUT_ROWMAJOR", "LAYOUT_TILE4", "LAYOUT_ZORDER",
 ]

@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 
 PERSPECTIVE, SPHERICAL, ORTHOGRAPHIC = 1, 2, 3          # main/hmap.cpp:104-106
 FP64_EXACT, FP32_FAST = 0, 1
-TRAVERSAL_AUTO, TRAVERSAL_BRUTE, TRAVERSAL_SKIP, TRAVERSAL_SKIP_FP64 = 0, 1, 2, 3
+TRAVERSAL_AUTO, TRAVERSAL_BRUTE, TRAVERSAL_SKIP, TRAVERSAL_SKIP_FP64, TRAVERSAL_PACK = 0, 1, 2, 3, 4
 FLAG_STATS, FLAG_STEP_INDEX, FLAG_RAY_DUMP = 1, 2, 4
 PIXEL_RGBA8, PIXEL_RGB8 = 0, 1
 LAYOUT_ROWMAJOR, LAYOUT_TILE4, LAYOUT_ZORDER = 0, 1, 2

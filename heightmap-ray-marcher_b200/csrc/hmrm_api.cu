@@ -23,6 +23,7 @@
 #include "k2_render_brute.cuh"
 #include "k2_render_skip.cuh"
 #include "k2_render_lin.cuh"
+#include "k2_render_pack.cuh"
 #include "peer_sync.cuh"
 #include "render_params.h"
 #include "synth_fbm.h"
@@ -516,7 +517,8 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 
 	int traversal = f->traversal;
 	if (traversal == HMRM_TRAVERSAL_AUTO) traversal = c->skip_ready ? HMRM_TRAVERSAL_SKIP : HMRM_TRAVERSAL_BRUTE;
-	if (traversal != HMRM_TRAVERSAL_BRUTE && traversal != HMRM_TRAVERSAL_SKIP && traversal != HMRM_TRAVERSAL_SKIP_FP64)
+	if (traversal != HMRM_TRAVERSAL_BRUTE && traversal != HMRM_TRAVERSAL_SKIP && traversal != HMRM_TRAVERSAL_SKIP_FP64 &&
+	    traversal != HMRM_TRAVERSAL_PACK)
 		return fail(c, HMRM_ERR_INVALID, "unknown traversal %d", f->traversal);
 	if (traversal != HMRM_TRAVERSAL_BRUTE) {
 		if (!c->skip_ready)
@@ -585,6 +587,22 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 		else if (c->layout == HMRM_LAYOUT_ZORDER) HMRM_LAUNCH_LIN(kLayoutZOrder);
 		else HMRM_LAUNCH_LIN(kLayoutRowMajor);
 #undef HMRM_LAUNCH_LIN
+	}
+	else if (traversal == HMRM_TRAVERSAL_PACK) {
+		const bool stats_kernel = want_stats || want_steps || want_dump;
+		const int lin_warps = HMRM_LIN_THREADS / 32;
+		int lin_blocks = c->num_sms * HMRM_LIN_CTAS;
+		if (lin_blocks > (n_tiles + lin_warps - 1) / lin_warps) lin_blocks = (n_tiles + lin_warps - 1) / lin_warps;
+		if (lin_blocks < 1) lin_blocks = 1;
+#define HMRM_LAUNCH_PACK(LAYOUT)                                                                              \
+		do {                                                                                                  \
+			if (stats_kernel) k2_render_pack<true, LAYOUT><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);   \
+			else k2_render_pack<false, LAYOUT><<<lin_blocks, HMRM_LIN_THREADS, 0, stream>>>(P);               \
+		} while (0)
+		if (c->layout == HMRM_LAYOUT_TILE4) HMRM_LAUNCH_PACK(kLayoutTile4);
+		else if (c->layout == HMRM_LAYOUT_ZORDER) HMRM_LAUNCH_PACK(kLayoutZOrder);
+		else HMRM_LAUNCH_PACK(kLayoutRowMajor);
+#undef HMRM_LAUNCH_PACK
 	}
 	else if (traversal == HMRM_TRAVERSAL_SKIP_FP64) {
 		if (want_stats || want_steps || want_dump) k2_render_skip<true><<<blocks, warps_per_block * 32, 0, stream>>>(P);

@@ -42,6 +42,8 @@ extern "C" {
 #define HMRM_TRAVERSAL_BRUTE 1   /* one height fetch per reference step (main/hmap.cpp:1000-1038 as written) */
 #define HMRM_TRAVERSAL_SKIP  2   /* conservative max-mip empty-space skip in whole steps (integer linear model; default) */
 #define HMRM_TRAVERSAL_SKIP_FP64 3   /* the same skip with exact FP64 positions at every decision (k2_render_skip.cuh) */
+#define HMRM_TRAVERSAL_PACK  4   /* HMRM_TRAVERSAL_SKIP's traversal with lanes refilled from a per-warp stack of rays
+                                  * (k2_render_pack.cuh) */
 
 /* hmrm_frame.flags */
 #define HMRM_FLAG_STATS      1u  /* count rays / steps / fetches (hmrm_get_stats) */

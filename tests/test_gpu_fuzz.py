@@ -102,7 +102,7 @@ def test_random_cases_match_oracle(hmrm, renderer, oracle, seed):
         a = renderer.render(fb).copy()
         sa, ia = renderer.stats(), renderer.step_index(fb)
         tag = f"seed {seed} case {i}: {fk} map {case['hm'].shape} lum {case['lum']} h [{case['min_height']},{case['max_height']}]"
-        for trav in (2, 3):
+        for trav in (2, 3, 4):
             fs = renderer.frame(traversal=trav, flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX, **fk)
             b = renderer.render(fs).copy()
             sb, ib = renderer.stats(), renderer.step_index(fs)
@@ -133,7 +133,7 @@ def check_against_oracle(hmrm, renderer, oracle, hm, cm, lum, mn, mx, fk, tag):
     heights = oracle.update_heightmap(hm, lum, mn, mx)
     want, osteps, ost = oracle.render(of, heights, cm)
     out = []
-    for trav in (1, 2, 3):
+    for trav in (1, 2, 3, 4):
         f = renderer.frame(traversal=trav, flags=hmrm.FLAG_STATS | hmrm.FLAG_STEP_INDEX, **fk)
         got = renderer.render(f).copy()
         st, si = renderer.stats(), renderer.step_index(f)

@@ -12,7 +12,7 @@ import scenes as S
 
 pytestmark = pytest.mark.gpu
 
-TRAVERSALS = [1, 2, 3]   # HMRM_TRAVERSAL_BRUTE, _SKIP (integer linear model), _SKIP_FP64
+TRAVERSALS = [1, 2, 3, 4]   # HMRM_TRAVERSAL_BRUTE, _SKIP (integer linear model), _SKIP_FP64, _PACK (refilled lanes)
 
 
 @pytest.mark.parametrize("traversal", TRAVERSALS)

@@ -25,7 +25,7 @@ def load_bench():
 # ---------------------------------------------------------------------------------------------------------------
 # N1: memory layout of the height pyramid never changes a result (same frames, step indices, steps AND fetches)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("traversal", [2, 3])
+@pytest.mark.parametrize("traversal", [2, 3, 4])
 @pytest.mark.parametrize("name", ["persp_graze", "spher_wide", "ortho_fine", "noise_lum_neg", "crop_ortho",
                                   "defaults_grid", "from_below", "tiny_res"])
 def test_pyramid_layouts_bit_exact(hmrm, oracle, name, traversal):
@@ -75,7 +75,7 @@ def test_layout_switch_needs_a_rebuilt_pyramid(hmrm, oracle):
 # ---------------------------------------------------------------------------------------------------------------
 # RGB8 frames = the RGBA8 frame without its constant alpha byte (main/hmap.cpp:139-154 always writes A = 255)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("traversal", [1, 2, 3])
+@pytest.mark.parametrize("traversal", [1, 2, 3, 4])
 @pytest.mark.parametrize("name", ["persp_basic", "spher_wide", "ortho_fine", "defaults_grid", "tiny_res", "alpha_zero_centre"])
 def test_rgb8_frame_is_the_rgba8_frame_without_alpha(hmrm, renderer, oracle, name, traversal):
     scene = S.SCENE_BY_NAME[name]          # widths 320, 384, 256 (word stores), 333 and 9 (byte stores)
@@ -145,7 +145,7 @@ def test_pixel_format_switch_starts_from_a_cleared_framebuffer(hmrm, renderer, o
 # ---------------------------------------------------------------------------------------------------------------
 # device-side intermediates against the reference's own functions (frames are blind to ulp-level errors)
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("traversal", [1, 2, 3])
+@pytest.mark.parametrize("traversal", [1, 2, 3, 4])
 def test_device_rays_match_reference_kat(hmrm, renderer, oracle, traversal):
     """ImagePlane::GetRay on the DEVICE (src/Perspective.cpp:25-32, src/Spherical.cpp:17-31,
     src/Orthographic.cpp:19-25): bit patterns of ray pos / dir at the reference's known-answer pixels."""

@@ -29,7 +29,7 @@ r.min_height, r.max_height = bench.MIN_HEIGHT, bench.MAX_HEIGHT
 if args.layout:
     r.set_layout({"rowmajor": 0, "tile4": 1, "zorder": 2}[args.layout])
 r.synth_maps(wl["log2n"], bench.SEED)
-trav = {"auto": 0, "brute": 1, "skip": 2, "skip_fp64": 3}[args.traversal]
+trav = {"auto": 0, "brute": 1, "skip": 2, "skip_fp64": 3, "pack": 4}[args.traversal]
 for i in range(args.frames):
     c = bench.camera(wl, args.first + i)
     if args.vang is not None:
