@@ -20,8 +20,11 @@
 // private to the warp.
 //
 // The exact FP64 anchor of a ray (k2_render_lin keeps it on the stack of every thread: 12.5 M sectors of L2 writes
-// per 4K frame) is not stored at all: the few samples that need the reference's own arithmetic rebuild it from the
-// pixel (generate_ray -> box_entry -> nudge -> advance_exact), in a non-inlined helper.
+// per 4K frame) is not stored at all.  A sample that needs the reference's own arithmetic (undecided in the model, or
+// the model's window ran out) takes the ray out of the march: a 3-word note (pixel, sample, level / reason) goes on a
+// second small list, and the next refill phase — where no lane holds live state — rebuilds the exact position from
+// the pixel (generate_ray -> box_entry -> nudge -> advance_exact), decides, and pushes the ray back with a fresh
+// model.  The march loop itself therefore contains no call and no FP64.
 #ifndef HMRM_K2_RENDER_PACK_CUH
 #define HMRM_K2_RENDER_PACK_CUH
 
@@ -35,7 +38,11 @@ namespace hmrm {
 #define HMRM_PACK_QCAP 64          // records per warp: <= 31 (parked / left over) + 32 (one tile) at any time
 #define HMRM_PACK_WORDS 16         // 32-bit words per record
 
-enum { kPackContinue = 0, kPackHit = 1, kPackMiss = 2, kPackCutOff = 3 };
+#define HMRM_PACK_SLOWCAP 32       // notes per warp: at most one per marching lane between two services
+
+enum { kPackContinue = 0, kPackHit = 1, kPackMiss = 2, kPackCutOff = 3, kPackSlow = 4 };
+// reasons of a note (bits 8.. of its level word)
+enum { kSlowDecide = 0x100, kSlowReanchor = 0x200 };
 
 // One ray in flight.  Everything else the march needs is derived from these (pack_derive).
 struct PackRay {
@@ -63,10 +70,8 @@ __device__ __forceinline__ PackDerived pack_derive(const RenderParams &P, const 
 }
 
 // The exact state of pixel `pixel` at sample 0: entry point + nudge, per-step addend (main/hmap.cpp:985-998, :1037).
-__device__ __forceinline__ void pack_exact_start(const RenderParams &P, unsigned pixel, AxisState &ax, AxisState &ay, AxisState &az) {
-	const Ray ray = generate_ray(P, (int)(pixel & 0xFFFFu), (int)(pixel >> 16));
-	double ex = 0.0, ey = 0.0, ez = 0.0, dist;
-	box_entry_at(P.c0, P.c1, ray, ex, ey, ez, dist);       // the ray is in flight: it entered
+__device__ __forceinline__ void pack_exact_start(const RenderParams &P, const Ray &ray, double ex, double ey, double ez,
+                                                 AxisState &ax, AxisState &ay, AxisState &az) {
 	ax.p = fadd(ex, fmul(P.nudge, ray.dx));
 	ay.p = fadd(ey, fmul(P.nudge, ray.dy));
 	az.p = fadd(ez, fmul(P.nudge, ray.dz));
@@ -75,6 +80,16 @@ __device__ __forceinline__ void pack_exact_start(const RenderParams &P, unsigned
 	az.s = fmul(P.step_dist, ray.dz);
 	ax.tag = ay.tag = az.tag = INT_MIN;
 	ax.S = ay.S = az.S = 0.0;
+}
+
+// Slopes of the integer model (k2_render_lin.cuh, fact 4); false if the ray does not fit it.
+__device__ __forceinline__ bool pack_slopes(const RenderParams &P, const AxisState &ax, const AxisState &ay, const AxisState &az, PackRay &r) {
+	const double zc = P.zq_offset - HMRM_MAGIC;
+	const double zs16 = P.zq_scale * 16.0;
+	bool model = lin_slope(ax.s * P.fx_scale, r.dx) && lin_slope(-ay.s * P.fx_scale, r.dy) && lin_slope(az.s * zs16, r.dz);
+	model = model && fabs(zc) < 1.0e12;
+	// no lateral motion and not coming down: such a ray can only end by the reference's hang; the per-step loop cuts it
+	return model && (r.dx != 0 || r.dy != 0 || r.dz < 0);
 }
 
 // Model offsets for the window that starts at the exact position (ax, ay, az); false if it left the representable range.
@@ -91,15 +106,11 @@ __device__ __forceinline__ bool pack_rebase(const RenderParams &P, const AxisSta
 	return okx && oky && okz;
 }
 
-// The plain per-step loop (k2_render_brute.cuh) for pixel `pixel` from sample `from` on: rays that do not fit the
-// integer model, and rays that left its representable range.  Returns kPackHit / kPackMiss / kPackCutOff.
+// The plain per-step loop (k2_render_brute.cuh) from the exact state (sample `from`) on: rays that do not fit the
+// integer model, and rays that left its representable range.  `steps` = samples examined (a hit is sample steps - 1).
 template <bool kStats>
-__device__ __noinline__ int pack_fallback(const RenderParams &P, unsigned pixel, unsigned from, unsigned &hit_cell,
-                                          unsigned long long &steps, unsigned &fetches) {
-	AxisState ax, ay, az;
-	pack_exact_start(P, pixel, ax, ay, az);
-	unsigned anchor = 0u;
-	advance_exact(ax, ay, az, anchor, from);
+__device__ __forceinline__ int pack_fallback(const RenderParams &P, AxisState &ax, AxisState &ay, AxisState &az, unsigned from,
+                                             unsigned &hit_cell, unsigned long long &steps, unsigned &fetches) {
 	unsigned long long kk = from;
 	int verdict = kPackMiss;
 	for (;;) {
@@ -120,20 +131,18 @@ __device__ __noinline__ int pack_fallback(const RenderParams &P, unsigned pixel,
 		}
 		ax.p = nx; ay.p = ny; az.p = nz;
 	}
-	steps = kk;        // a hit at sample kk - 1 (first_hit), otherwise kk samples were examined
+	steps = kk;
 	return verdict;
 }
 
-// A sample the integer model cannot decide: the reference's own expressions (main/hmap.cpp:1001-1016) on the exact
-// FP64 sample, rebuilt from the pixel.  First an FP64 linear look from sample 0 (P_n = P_0 + n s up to the roundings
-// of the reference's n adds: |P_n - fma(n, s, P_0)| <= (n + 1) 2^-53 max|P|, doubled below), which decides unless the
-// sample is within ~1e-10 of a cell edge or of the surface; then the exact reconstruction.
+// A sample the integer model could not decide: the reference's own expressions (main/hmap.cpp:1001-1016).  First an
+// FP64 linear look from sample 0 (P_n = P_0 + n s up to the roundings of the reference's n adds:
+// |P_n - fma(n, s, P_0)| <= (n + 1) 2^-53 max|P|, doubled below), which decides unless the sample is within ~1e-10
+// of a cell edge or of the surface; then the exact reconstruction (advance_exact moves the anchor to sample n).
 // Returns kPackHit (hit_cell set), kPackMiss (left the grid) or kPackContinue (not below the surface).
 template <bool kStats>
-__device__ __noinline__ int pack_decide_exact(const RenderParams &P, unsigned pixel, unsigned n, unsigned &hit_cell, unsigned &fetches,
-                                              unsigned *dbg_exact) {
-	AxisState ax, ay, az;
-	pack_exact_start(P, pixel, ax, ay, az);
+__device__ __forceinline__ int pack_decide_exact(const RenderParams &P, AxisState &ax, AxisState &ay, AxisState &az, unsigned &anchor,
+                                                 unsigned n, unsigned &hit_cell, unsigned &fetches, unsigned &exact_used) {
 	{
 		const double mj = (double)n;
 		const double rel = fmul(fadd(mj, 2.0), 2.3e-16);
@@ -159,8 +168,7 @@ __device__ __noinline__ int pack_decide_exact(const RenderParams &P, unsigned pi
 			if (fsub(ze, bz) > surf) return kPackContinue;
 		}
 	}
-	if (kStats && dbg_exact) *dbg_exact += 1u;
-	unsigned anchor = 0u;
+	exact_used = 1u;
 	advance_exact(ax, ay, az, anchor, n);
 	const int gx = trunc_cell(fdiv(ax.p, P.gw)), gy = trunc_cell(fdiv(-ay.p, P.gw));
 	if (gx < 0 || gy < 0 || gx >= P.map_w || gy >= P.map_h) return kPackMiss;
@@ -173,36 +181,16 @@ __device__ __noinline__ int pack_decide_exact(const RenderParams &P, unsigned pi
 	return kPackContinue;
 }
 
-// Re-anchor the model on the exact position of sample n (keeps the error bound of fact 4); false if the position
-// left the representable range (the caller finishes with the per-step loop).
-__device__ __noinline__ bool pack_reanchor(const RenderParams &P, PackRay &r) {
-	AxisState ax, ay, az;
-	pack_exact_start(P, r.pixel, ax, ay, az);
-	unsigned anchor = 0u;
-	advance_exact(ax, ay, az, anchor, r.n);
-	return pack_rebase(P, ax, ay, az, r);
-}
-
 // One iteration of the traversal for the ray in `r` (the loop body of march_lin, k2_render_lin.cuh, on the same
-// model, with the same margins).  kPackContinue: r advanced to its next sample.
+// model, with the same margins).  kPackContinue: r advanced to its next sample.  kPackSlow: the sample r.n needs the
+// exact arithmetic (r.level carries the reason); the ray leaves the march until the next refill phase.
 template <bool kStats, int kLayout>
 __device__ __forceinline__ int pack_iterate(const RenderParams &P, PackRay &r, const PackDerived &dv, unsigned &hit_cell,
                                             unsigned &fetches, unsigned *dbg) {
 	const int k = P.fx_bits;
 	const int cell_mask = (1 << k) - 1;
 	// window of the model: V_0 is the exact sample `base`, a multiple of the period (jumps never cross one)
-	unsigned base = r.n & ~(HMRM_LIN_PERIOD - 1u);
-	if (r.level < 0) {
-		// the previous iteration ended exactly on a window boundary: re-anchor there
-		r.level = -r.level - 1;
-		if (r.n >= 0x7FF00000u) return kPackCutOff;          // ~2^31 samples: give up like a hang would, but flagged
-		if (!pack_reanchor(P, r)) {
-			unsigned long long steps = 0ULL;
-			const int v = pack_fallback<kStats>(P, r.pixel, r.n, hit_cell, steps, fetches);
-			r.n = (unsigned)min(steps, 0xFFFFFFFFULL);
-			return v == kPackHit ? kPackHit + 4 : v;         // + 4: r.n already counts the hit sample
-		}
-	}
+	const unsigned base = r.n & ~(HMRM_LIN_PERIOD - 1u);
 	const unsigned j = r.n - base;
 	LinAxis lx, ly, lz;
 	lx.d = r.dx; lx.a0 = r.ax;
@@ -288,253 +276,350 @@ __device__ __forceinline__ int pack_iterate(const RenderParams &P, PackRay &r, c
 		return kPackHit;
 	}
 	else {
-		const int v = pack_decide_exact<kStats>(P, r.pixel, r.n, hit_cell, fetches, kStats ? &dbg[7] : NULL);
-		if (v != kPackContinue) {
-			if (kStats && v == kPackHit) dbg[5] += 1u;
-			return v;
-		}
-		if (kStats) dbg[4] += 1u;
-		level = 0;
+		r.level = kSlowDecide;          // undecided: sample r.n goes to the exact arithmetic; the march resumes at level 0
+		return kPackSlow;
 	}
 	r.n += m;
-	// a sample on a window boundary needs the model re-anchored before it is examined: flagged in the sign of level
-	r.level = ((r.n & (HMRM_LIN_PERIOD - 1u)) == 0u) ? -level - 1 : level;
+	r.level = level;
+	if ((r.n & (HMRM_LIN_PERIOD - 1u)) == 0u) {
+		r.level = kSlowReanchor | level;    // the window ran out: a fresh model anchored on the exact sample r.n
+		return kPackSlow;
+	}
 	return kPackContinue;
 }
 
-template <bool kStats, int kLayout>
-__global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_pack(const __grid_constant__ RenderParams P) {
-	__shared__ unsigned s_queue[HMRM_LIN_THREADS / 32][HMRM_PACK_WORDS][HMRM_PACK_QCAP];
-	const int lane = threadIdx.x & 31;
-	unsigned(*Q)[HMRM_PACK_QCAP] = s_queue[threadIdx.x >> 5];
-	const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
-	const unsigned lt_mask = (1u << lane) - 1u;
+typedef unsigned (*PackQueue)[HMRM_PACK_QCAP];
 
-	auto put = [&](int slot, const PackRay &r) {
-		Q[0][slot] = (unsigned)r.dx; Q[1][slot] = (unsigned)((unsigned long long)r.dx >> 32);
-		Q[2][slot] = (unsigned)r.dy; Q[3][slot] = (unsigned)((unsigned long long)r.dy >> 32);
-		Q[4][slot] = (unsigned)r.dz; Q[5][slot] = (unsigned)((unsigned long long)r.dz >> 32);
-		Q[6][slot] = (unsigned)r.ax; Q[7][slot] = (unsigned)((unsigned long long)r.ax >> 32);
-		Q[8][slot] = (unsigned)r.ay; Q[9][slot] = (unsigned)((unsigned long long)r.ay >> 32);
-		Q[10][slot] = (unsigned)r.az; Q[11][slot] = (unsigned)((unsigned long long)r.az >> 32);
-		Q[12][slot] = r.pixel;
-		Q[13][slot] = r.n;
-		Q[14][slot] = (unsigned)r.level;
-		Q[15][slot] = r.miss_rgba;
-	};
-	auto get = [&](int slot, PackRay &r) {
-		r.dx = (long long)((unsigned long long)Q[0][slot] | ((unsigned long long)Q[1][slot] << 32));
-		r.dy = (long long)((unsigned long long)Q[2][slot] | ((unsigned long long)Q[3][slot] << 32));
-		r.dz = (long long)((unsigned long long)Q[4][slot] | ((unsigned long long)Q[5][slot] << 32));
-		r.ax = (long long)((unsigned long long)Q[6][slot] | ((unsigned long long)Q[7][slot] << 32));
-		r.ay = (long long)((unsigned long long)Q[8][slot] | ((unsigned long long)Q[9][slot] << 32));
-		r.az = (long long)((unsigned long long)Q[10][slot] | ((unsigned long long)Q[11][slot] << 32));
-		r.pixel = Q[12][slot];
-		r.n = Q[13][slot];
-		r.level = (int)Q[14][slot];
-		r.miss_rgba = Q[15][slot];
-	};
-	// one finished pixel (any lane, any time): main/hmap.cpp:139-154
-	auto store_one = [&](unsigned pixel, uint32_t rgba, int first_hit) {
-		const size_t at = (size_t)(pixel >> 16) * (size_t)P.W + (size_t)(pixel & 0xFFFFu);
-		if (P.pixel_format == 0) P.fb[HMRM_CHECKED(P, at, (size_t)P.W * (size_t)P.H)] = rgba;
+__device__ __forceinline__ void pack_put(PackQueue Q, int slot, const PackRay &r) {
+	Q[0][slot] = (unsigned)r.dx; Q[1][slot] = (unsigned)((unsigned long long)r.dx >> 32);
+	Q[2][slot] = (unsigned)r.dy; Q[3][slot] = (unsigned)((unsigned long long)r.dy >> 32);
+	Q[4][slot] = (unsigned)r.dz; Q[5][slot] = (unsigned)((unsigned long long)r.dz >> 32);
+	Q[6][slot] = (unsigned)r.ax; Q[7][slot] = (unsigned)((unsigned long long)r.ax >> 32);
+	Q[8][slot] = (unsigned)r.ay; Q[9][slot] = (unsigned)((unsigned long long)r.ay >> 32);
+	Q[10][slot] = (unsigned)r.az; Q[11][slot] = (unsigned)((unsigned long long)r.az >> 32);
+	Q[12][slot] = r.pixel;
+	Q[13][slot] = r.n;
+	Q[14][slot] = (unsigned)r.level;
+	Q[15][slot] = r.miss_rgba;
+}
+
+__device__ __forceinline__ void pack_get(PackQueue Q, int slot, PackRay &r) {
+	r.dx = (long long)((unsigned long long)Q[0][slot] | ((unsigned long long)Q[1][slot] << 32));
+	r.dy = (long long)((unsigned long long)Q[2][slot] | ((unsigned long long)Q[3][slot] << 32));
+	r.dz = (long long)((unsigned long long)Q[4][slot] | ((unsigned long long)Q[5][slot] << 32));
+	r.ax = (long long)((unsigned long long)Q[6][slot] | ((unsigned long long)Q[7][slot] << 32));
+	r.ay = (long long)((unsigned long long)Q[8][slot] | ((unsigned long long)Q[9][slot] << 32));
+	r.az = (long long)((unsigned long long)Q[10][slot] | ((unsigned long long)Q[11][slot] << 32));
+	r.pixel = Q[12][slot];
+	r.n = Q[13][slot];
+	r.level = (int)Q[14][slot];
+	r.miss_rgba = Q[15][slot];
+}
+
+// statistics of one finished ray; per-lane atomics: the counting variant is not the timed one
+template <bool kStats>
+__device__ __forceinline__ void pack_tally(const RenderParams &P, bool surf_hit, unsigned long long steps, bool cut) {
+	if (cut) atomicOr(&P.stats->status, 4u);
+	if (!kStats) return;
+	atomicAdd(&P.stats->box_hits, 1ULL);
+	if (surf_hit) atomicAdd(&P.stats->surf_hits, 1ULL);
+	atomicAdd(&P.stats->steps, steps);
+	atomicMax(&P.stats->max_steps, steps);
+}
+
+// (kStats) fetch and event counters of the part of a ray marched so far: flushed whenever the ray changes hands
+__device__ __forceinline__ void pack_flush_counters(const RenderParams &P, unsigned &fetches, unsigned *dbg) {
+	if (fetches) atomicAdd(&P.stats->fetches, (unsigned long long)fetches);
+	fetches = 0u;
+	for (int i = 0; i < 8; ++i) {
+		if (dbg[i]) atomicAdd(&P.stats->dbg[i], (unsigned long long)dbg[i]);
+		dbg[i] = 0u;
+	}
+}
+
+// one finished pixel (any lane, any time): main/hmap.cpp:139-154
+__device__ __forceinline__ void pack_store(const RenderParams &P, unsigned pixel, uint32_t rgba, int first_hit) {
+	const size_t at = (size_t)(pixel >> 16) * (size_t)P.W + (size_t)(pixel & 0xFFFFu);
+	if (P.pixel_format == 0) P.fb[HMRM_CHECKED(P, at, (size_t)P.W * (size_t)P.H)] = rgba;
+	else {
+		uint8_t *o = (uint8_t *)P.fb + HMRM_CHECKED(P, at * 3, (size_t)P.W * (size_t)P.H * 3);
+		o[0] = (uint8_t)rgba;
+		o[1] = (uint8_t)(rgba >> 8);
+		o[2] = (uint8_t)(rgba >> 16);
+	}
+	if (P.step_index) P.step_index[at] = first_hit;
+}
+
+// REFILL: the warp, with all 32 lanes free and nothing in flight, (1) serves the notes of rays that asked for the
+// exact arithmetic — one note per lane — and (2) sets up tiles until its stack holds at least 32 rays or the frame has
+// no more tiles.  Pixels that miss the box (or end in the service) are finished here; rays that go on are pushed.
+// Not inlined: the FP64-heavy code gets its own register allocation instead of competing with the march loop's.
+// io: [0] stack count, [1] cur, [2] end (tile queue batch), [3] tiles_left, [4] notes.
+template <bool kStats>
+__device__ __noinline__ void pack_refill(const RenderParams &P, PackQueue Q, const unsigned (*S)[HMRM_PACK_SLOWCAP], unsigned io[5]) {
+	const int lane = threadIdx.x & 31;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const unsigned n_tiles = (unsigned)(P.tiles_x * P.tiles_y);
+	int count = (int)io[0];
+	unsigned cur = io[1], end = io[2];
+	bool tiles_left = io[3] != 0u;
+	int notes = (int)io[4];
+
+	// `first` pass: the notes (at most 32, one per lane); then tiles
+	for (;;) {
+		const bool serving = notes > 0;
+		if (!serving && !(count < 32 && tiles_left)) break;
+		bool selected = false;
+		int px = 0, py = 0;
+		unsigned at_n = 0u;          // sample the ray (re)starts at
+		int level = P.lstart;
+		int reason = 0;
+		if (serving) {
+			if (lane < notes) {
+				const unsigned pixel = S[0][lane];
+				px = (int)(pixel & 0xFFFFu);
+				py = (int)(pixel >> 16);
+				at_n = S[1][lane];
+				reason = (int)S[2][lane] & ~0xFF;
+				level = (int)S[2][lane] & 0xFF;
+				selected = true;
+			}
+			notes = 0;
+		}
 		else {
-			uint8_t *o = (uint8_t *)P.fb + HMRM_CHECKED(P, at * 3, (size_t)P.W * (size_t)P.H * 3);
-			o[0] = (uint8_t)rgba;
-			o[1] = (uint8_t)(rgba >> 8);
-			o[2] = (uint8_t)(rgba >> 16);
+			if (cur == end) {
+				// (marching tiles are grabbed one at a time, the sky rows at the end of the schedule 8 at a time:
+				// k2_render_lin.cuh)
+				const unsigned batch = (end != 0u && end >= P.batch_from_tile) ? 8u : 1u;
+				unsigned t = 0u;
+				if (lane == 0) t = atomicAdd(P.tile_counter, batch);
+				cur = __shfl_sync(0xFFFFFFFFu, t, 0);
+				end = min(cur + batch, n_tiles);
+				if (cur >= n_tiles) {
+					tiles_left = false;
+					break;
+				}
+			}
+			const unsigned tile = cur++;
+			int ty_seq, tx;
+			tile_row_col(P, tile, ty_seq, tx);
+			const int ty = P.row_order ? __ldg(P.row_order + HMRM_CHECKED(P, ty_seq, P.tiles_y)) : ty_seq;
+			px = tx * 8 + (lane & 7);
+			py = P.row_begin + (P.tile_y_first + ty * P.tile_y_step) * 4 + (lane >> 3);
+			selected = pixel_selected(P, px, py);
 		}
-		if (P.step_index) P.step_index[at] = first_hit;
-	};
-	auto tally_ray = [&](bool surf_hit, unsigned long long steps, unsigned fetches, bool cut, const unsigned *dbg) {
-		if (!kStats) {
-			if (cut) atomicOr(&P.stats->status, 4u);
-			return;
+		bool push = false;
+		bool resolved = false;       // a pixel of a fresh tile finished at set-up (stored by rows below)
+		uint32_t rgba = 0u;
+		PackRay nr;
+		nr.dx = nr.dy = nr.dz = nr.ax = nr.ay = nr.az = 0;
+		nr.pixel = (unsigned)px | ((unsigned)py << 16);
+		nr.n = at_n;
+		nr.level = level;
+		nr.miss_rgba = 0u;
+		if (selected) {
+			const Ray gr = generate_ray(P, px, py);
+			double ex = 0.0, ey = 0.0, ez = 0.0, dist = 0.0;
+			// (a note's ray did enter the box: run the slab test itself, not the shortcut that only proves a miss)
+			const bool entered = serving ? box_entry_at(P.c0, P.c1, gr, ex, ey, ez, dist) : box_entry(P, gr, ex, ey, ez, dist);
+			if (kStats && !serving && P.ray_dump) dump_ray(P, px, py, gr, entered, dist, ex, ey, ez);
+			rgba = miss_colour(P, gr.dz);
+			if (kStats && !serving) atomicAdd(&P.stats->rays, 1ULL);
+			if (!entered) {
+				resolved = true;
+				if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = -1;
+			}
+			else {
+				AxisState ax, ay, az;
+				pack_exact_start(P, gr, ex, ey, ez, ax, ay, az);
+				unsigned anchor = 0u;          // sample index of (ax.p, ay.p, az.p)
+				unsigned hit_cell = 0u, f = 0u, exact_used = 0u;
+				int verdict = kPackContinue;   // of this refill: kPackContinue = the ray goes (back) on the stack
+				unsigned long long steps = 0ULL;
+				bool counted = false;          // `steps` already counts the hit sample
+				if (reason == kSlowDecide) {
+					verdict = pack_decide_exact<kStats>(P, ax, ay, az, anchor, at_n, hit_cell, f, exact_used);
+					steps = at_n;
+					if (verdict == kPackContinue) {
+						nr.n = at_n + 1u;          // not below the surface: a plain step, cell level next
+						nr.level = 0;
+						if (kStats) atomicAdd(&P.stats->dbg[4], 1ULL);
+					}
+					else if (kStats && verdict == kPackHit) atomicAdd(&P.stats->dbg[5], 1ULL);
+					if (kStats && exact_used) atomicAdd(&P.stats->dbg[7], 1ULL);
+				}
+				if (verdict == kPackContinue && nr.n >= 0x7FF00000u && (nr.n & (HMRM_LIN_PERIOD - 1u)) == 0u) {
+					verdict = kPackCutOff;         // ~2^31 samples: give up like a hang would, but flagged
+					steps = nr.n;
+				}
+				if (verdict == kPackContinue) {
+					// (re)build the integer model for the window that contains nr.n, anchored on its exact first sample
+					bool model = pack_slopes(P, ax, ay, az, nr);
+					if (model) {
+						advance_exact(ax, ay, az, anchor, nr.n & ~(HMRM_LIN_PERIOD - 1u));
+						model = pack_rebase(P, ax, ay, az, nr);
+					}
+					nr.miss_rgba = rgba;
+					push = model;
+					if (!model) {
+						// does not fit the model (or left its range): the per-step loop from sample nr.n, right here
+						advance_exact(ax, ay, az, anchor, nr.n);
+						verdict = pack_fallback<kStats>(P, ax, ay, az, nr.n, hit_cell, steps, f);
+						counted = true;
+					}
+				}
+				if (kStats && f) atomicAdd(&P.stats->fetches, (unsigned long long)f);
+				if (verdict != kPackContinue) {
+					int first_hit = -2;
+					if (verdict == kPackHit) {
+						rgba = hit_colour(P, __ldg(P.color + HMRM_CHECKED(P, hit_cell, (size_t)P.map_w * (size_t)P.map_h)));
+						const unsigned long long at = counted ? steps - 1ULL : steps;
+						first_hit = (at > 0x7FFFFFFFULL) ? 0x7FFFFFFF : (int)at;
+						if (!counted) steps += 1ULL;
+					}
+					pack_tally<kStats>(P, verdict == kPackHit, steps, verdict == kPackCutOff);
+					if (serving) pack_store(P, nr.pixel, rgba, first_hit);
+					else {
+						if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
+						resolved = true;
+					}
+				}
+			}
 		}
-		atomicAdd(&P.stats->box_hits, 1ULL);
-		if (surf_hit) atomicAdd(&P.stats->surf_hits, 1ULL);
-		atomicAdd(&P.stats->steps, steps);
-		atomicAdd(&P.stats->fetches, (unsigned long long)fetches);
-		atomicMax(&P.stats->max_steps, steps);
-		if (cut) atomicOr(&P.stats->status, 4u);
-		for (int i = 0; i < 8; ++i) {
-			if (dbg[i]) atomicAdd(&P.stats->dbg[i], (unsigned long long)dbg[i]);
-		}
-	};
+		// finished pixels of a fresh tile: whole rows as words where possible (ray_setup.cuh)
+		if (!serving) store_pixel(P, px, py, resolved, rgba);
+		const unsigned pm = __ballot_sync(0xFFFFFFFFu, push);
+		if (push) pack_put(Q, count + __popc(pm & lt_mask), nr);
+		count += __popc(pm);
+		__syncwarp();
+	}
+	io[0] = (unsigned)count;
+	io[1] = cur;
+	io[2] = end;
+	io[3] = tiles_left ? 1u : 0u;
+	io[4] = 0u;
+}
+
+#ifndef HMRM_PACK_CTAS
+#define HMRM_PACK_CTAS HMRM_LIN_CTAS
+#endif
+
+template <bool kStats, int kLayout>
+__global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_PACK_CTAS) k2_render_pack(const __grid_constant__ RenderParams P) {
+	__shared__ unsigned s_queue[HMRM_LIN_THREADS / 32][HMRM_PACK_WORDS][HMRM_PACK_QCAP];
+	__shared__ unsigned s_slow[HMRM_LIN_THREADS / 32][3][HMRM_PACK_SLOWCAP];
+	__shared__ unsigned s_tiles[HMRM_LIN_THREADS / 32][2];       // per warp: cur, end of its tile-queue batch
+	const int lane = threadIdx.x & 31;
+	PackQueue Q = s_queue[threadIdx.x >> 5];
+	unsigned(*S)[HMRM_PACK_SLOWCAP] = s_slow[threadIdx.x >> 5];
+	unsigned *tq = s_tiles[threadIdx.x >> 5];
+	const unsigned lt_mask = (1u << lane) - 1u;
+	if (lane == 0) { tq[0] = 0u; tq[1] = 0u; }
+	__syncwarp();
 
 	int count = 0;                 // records on this warp's stack (warp-uniform)
-	bool has = false;              // this lane holds a ray
-	PackRay ray;
-	PackDerived dv;
-	unsigned fetches = 0u;         // (kStats) fetches of the ray in flight; parked rays keep theirs in the tally
-	unsigned dbg[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-	ray.dx = ray.dy = ray.dz = ray.ax = ray.ay = ray.az = 0;
-	ray.pixel = ray.n = 0u;
-	ray.level = 0;
-	ray.miss_rgba = 0u;
-	dv.inv_adx = dv.inv_ady = dv.inv_adz = 0.f;
-	dv.cell_exit = 0;
-
-	unsigned cur = 0u, end = 0u;
+	int notes = 0;                 // rays waiting for the exact arithmetic (warp-uniform)
 	bool tiles_left = true;
-	for (;;) {
-		// ---- idle lanes pop ----
-		unsigned active = __ballot_sync(0xFFFFFFFFu, has);
-		if (count > 0 && active != 0xFFFFFFFFu) {
-			const unsigned idle = ~active;
-			const int rank = __popc(idle & lt_mask);
-			const int take = min(__popc(idle), count);
-			if (!has && rank < take) {
-				get(count - 1 - rank, ray);
-				dv = pack_derive(P, ray);
-				has = true;
-			}
-			count -= take;
-			__syncwarp();
-			active = __ballot_sync(0xFFFFFFFFu, has);
-		}
-		const int n_active = __popc(active);
 
-		// ---- produce: only when lanes would idle, and with every lane free ----
-		if (count == 0 && n_active <= HMRM_PACK_THRESH && tiles_left) {
-			if (has) {                                   // park: records are resumable
-				put(__popc(active & lt_mask), ray);
-				if (kStats) {
-					// counters of the part marched so far go to the tally now
-					atomicAdd(&P.stats->fetches, (unsigned long long)fetches);
-					for (int i = 0; i < 8; ++i) {
-						if (dbg[i]) atomicAdd(&P.stats->dbg[i], (unsigned long long)dbg[i]);
-						dbg[i] = 0u;
-					}
-					fetches = 0u;
-				}
-				has = false;
-			}
-			// (dead values from here on: lets the register allocator reuse them for the set-up code below)
-			ray.dx = ray.dy = ray.dz = ray.ax = ray.ay = ray.az = 0;
-			ray.pixel = ray.n = 0u;
-			ray.level = 0;
-			ray.miss_rgba = 0u;
-			dv.inv_adx = dv.inv_ady = dv.inv_adz = 0.f;
-			dv.cell_exit = 0;
-			count = n_active;
+	// Outer loop: refill, then march.  The state of the rays in flight is declared INSIDE the march phase, so that
+	// nothing of it is live across the refill call (a value live across a call lives on the stack — for the whole
+	// loop).
+	for (;;) {
+		{
+			unsigned io[5] = {(unsigned)count, tq[0], tq[1], tiles_left ? 1u : 0u, (unsigned)notes};
+			pack_refill<kStats>(P, Q, S, io);
+			count = (int)io[0];
+			if (lane == 0) { tq[0] = io[1]; tq[1] = io[2]; }
+			tiles_left = io[3] != 0u;
+			notes = 0;
 			__syncwarp();
-			while (count < 32 && tiles_left) {
-				if (cur == end) {
-					const unsigned batch = (end != 0u && end >= P.batch_from_tile) ? 8u : 1u;
-					unsigned t = 0u;
-					if (lane == 0) t = atomicAdd(P.tile_counter, batch);
-					cur = __shfl_sync(0xFFFFFFFFu, t, 0);
-					end = min(cur + batch, n_tiles);
-					if (cur >= n_tiles) {
-						tiles_left = false;
-						break;
-					}
+		}
+		if (count == 0 && !tiles_left) break;
+
+		bool has = false;              // this lane holds a ray
+		PackRay ray;
+		PackDerived dv;
+		unsigned fetches = 0u;         // (kStats) counters of the ray in flight
+		unsigned dbg[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+		ray.dx = ray.dy = ray.dz = ray.ax = ray.ay = ray.az = 0;
+		ray.pixel = ray.n = 0u;
+		ray.level = 0;
+		ray.miss_rgba = 0u;
+		dv.inv_adx = dv.inv_ady = dv.inv_adz = 0.f;
+		dv.cell_exit = 0;
+		for (;;) {
+			// ---- idle lanes pop ----
+			unsigned active = __ballot_sync(0xFFFFFFFFu, has);
+			if (count > 0 && active != 0xFFFFFFFFu) {
+				const unsigned idle = ~active;
+				const int rank = __popc(idle & lt_mask);
+				const int take = min(__popc(idle), count);
+				if (!has && rank < take) {
+					pack_get(Q, count - 1 - rank, ray);
+					dv = pack_derive(P, ray);
+					has = true;
 				}
-				const unsigned tile = cur++;
-				int ty_seq, tx;
-				tile_row_col(P, tile, ty_seq, tx);
-				const int ty = P.row_order ? __ldg(P.row_order + HMRM_CHECKED(P, ty_seq, P.tiles_y)) : ty_seq;
-				const int px = tx * 8 + (lane & 7);
-				const int py = P.row_begin + (P.tile_y_first + ty * P.tile_y_step) * 4 + (lane >> 3);
-				const bool selected = pixel_selected(P, px, py);
-				bool push = false;
-				bool resolved = false;       // pixel finished at set-up
-				uint32_t rgba = 0u;
-				PackRay nr;
-				nr.dx = nr.dy = nr.dz = nr.ax = nr.ay = nr.az = 0;
-				nr.pixel = (unsigned)px | ((unsigned)py << 16);
-				nr.n = 0u;
-				nr.level = P.lstart;
-				nr.miss_rgba = 0u;
-				if (selected) {
-					const Ray gr = generate_ray(P, px, py);
-					double ex, ey, ez, dist = 0.0;
-					const bool entered = box_entry(P, gr, ex, ey, ez, dist);
-					if (kStats && P.ray_dump) dump_ray(P, px, py, gr, entered, dist, ex, ey, ez);
-					rgba = miss_colour(P, gr.dz);
-					if (kStats) atomicAdd(&P.stats->rays, 1ULL);
-					if (!entered) {
-						resolved = true;
-						if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = -1;
-					}
-					else {
-						// the integer model of this ray (k2_render_lin.cuh, fact 4)
-						AxisState ax, ay, az;
-						ax.p = fadd(ex, fmul(P.nudge, gr.dx));
-						ay.p = fadd(ey, fmul(P.nudge, gr.dy));
-						az.p = fadd(ez, fmul(P.nudge, gr.dz));
-						ax.s = fmul(P.step_dist, gr.dx);
-						ay.s = fmul(P.step_dist, gr.dy);
-						az.s = fmul(P.step_dist, gr.dz);
-						const double zc = P.zq_offset - HMRM_MAGIC;
-						const double zs16 = P.zq_scale * 16.0;
-						bool model = lin_slope(ax.s * P.fx_scale, nr.dx) && lin_slope(-ay.s * P.fx_scale, nr.dy) && lin_slope(az.s * zs16, nr.dz);
-						model = model && fabs(zc) < 1.0e12;
-						model = model && (nr.dx != 0 || nr.dy != 0 || nr.dz < 0);
-						model = model && pack_rebase(P, ax, ay, az, nr);
-						nr.miss_rgba = rgba;
-						push = model;
-						if (!model) {
-							// does not fit the model: the per-step loop, right here
-							unsigned cell = 0u, f = 0u;
-							unsigned long long steps = 0ULL;
-							const int v = pack_fallback<kStats>(P, nr.pixel, 0u, cell, steps, f);
-							int first_hit = -2;
-							if (v == kPackHit) {
-								rgba = hit_colour(P, __ldg(P.color + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h)));
-								first_hit = (steps - 1ULL > 0x7FFFFFFFULL) ? 0x7FFFFFFF : (int)(steps - 1ULL);
-							}
-							const unsigned none[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-							tally_ray(v == kPackHit, steps, f, v == kPackCutOff, none);
-							if (P.step_index) P.step_index[(size_t)py * (size_t)P.W + (size_t)px] = first_hit;
-							resolved = true;
-						}
-					}
+				count -= take;
+				__syncwarp();
+				active = __ballot_sync(0xFFFFFFFFu, has);
+			}
+			const int n_active = __popc(active);
+
+			// ---- back to the refill phase: when lanes would idle (or the notes could overflow), with every lane free ----
+			const bool want_refill = (count == 0 && n_active <= HMRM_PACK_THRESH && (tiles_left || notes > 0)) ||
+			                         notes + n_active > HMRM_PACK_SLOWCAP;
+			if (want_refill || n_active == 0) {
+				if (has) {                               // park: records are resumable
+					pack_put(Q, count + __popc(active & lt_mask), ray);
+					if (kStats) pack_flush_counters(P, fetches, dbg);
 				}
-				// finished pixels of the tile (misses): whole rows as words where possible (ray_setup.cuh)
-				store_pixel(P, px, py, resolved, rgba);
-				const unsigned pm = __ballot_sync(0xFFFFFFFFu, push);
-				if (push) put(count + __popc(pm & lt_mask), nr);
-				count += __popc(pm);
+				count += n_active;
+				__syncwarp();
+				break;
+			}
+
+			// ---- march: one iteration for every lane that holds a ray ----
+			bool slow = false;
+			if (has) {
+				unsigned hit_cell = 0u;
+				const int v = pack_iterate<kStats, kLayout>(P, ray, dv, hit_cell, fetches, dbg);
+				if (v == kPackSlow) {
+					slow = true;
+					has = false;
+					if (kStats) pack_flush_counters(P, fetches, dbg);
+				}
+				else if (v != kPackContinue) {
+					uint32_t rgba = ray.miss_rgba;
+					int first_hit = -2;
+					unsigned long long steps = ray.n;
+					if (v == kPackHit) {
+						rgba = hit_colour(P, __ldg(P.color + HMRM_CHECKED(P, hit_cell, (size_t)P.map_w * (size_t)P.map_h)));
+						first_hit = (steps > 0x7FFFFFFFULL) ? 0x7FFFFFFF : (int)steps;
+						steps += 1ULL;
+					}
+					pack_store(P, ray.pixel, rgba, first_hit);
+					pack_tally<kStats>(P, v == kPackHit, steps, v == kPackCutOff);
+					if (kStats) pack_flush_counters(P, fetches, dbg);
+					has = false;
+				}
+			}
+			// rays that asked for the exact arithmetic leave a note (the SLOWCAP test above guarantees the room)
+			const unsigned sm = __ballot_sync(0xFFFFFFFFu, slow);
+			if (sm) {
+				if (slow) {
+					const int at = notes + __popc(sm & lt_mask);
+					S[0][at] = ray.pixel;
+					S[1][at] = ray.n;
+					S[2][at] = (unsigned)ray.level;
+				}
+				notes += __popc(sm);
 				__syncwarp();
 			}
-			continue;
-		}
-		if (n_active == 0) {
-			if (count == 0 && !tiles_left) break;
-			continue;
-		}
-
-		// ---- march: one iteration for every lane that holds a ray ----
-		if (has) {
-			unsigned hit_cell = 0u;
-			int v = pack_iterate<kStats, kLayout>(P, ray, dv, hit_cell, fetches, dbg);
-			if (v != kPackContinue) {
-				const bool counted = v >= 4;              // the per-step loop already counted the hit sample
-				if (counted) v -= 4;
-				uint32_t rgba = ray.miss_rgba;
-				int first_hit = -2;
-				unsigned long long steps = ray.n;
-				if (v == kPackHit) {
-					rgba = hit_colour(P, __ldg(P.color + HMRM_CHECKED(P, hit_cell, (size_t)P.map_w * (size_t)P.map_h)));
-					const unsigned long long at = counted ? steps - 1ULL : steps;
-					first_hit = (at > 0x7FFFFFFFULL) ? 0x7FFFFFFF : (int)at;
-					if (!counted) steps += 1ULL;
-				}
-				store_one(ray.pixel, rgba, first_hit);
-				tally_ray(v == kPackHit, steps, fetches, v == kPackCutOff, dbg);
-				if (kStats) {
-					fetches = 0u;
-					for (int i = 0; i < 8; ++i) dbg[i] = 0u;
-				}
-				has = false;
+			if (kStats && lane == __ffs(active) - 1) {
+				// [6]: warp-level march iterations; [8..11]: by busy lanes (1-8, 9-16, 17-24, 25-32)
+				atomicAdd(&P.stats->dbg[6], 1ULL);
+				atomicAdd(&P.stats->dbg[8 + ((n_active - 1) >> 3)], 1ULL);
 			}
-		}
-		if (kStats && lane == __ffs(active) - 1) {
-			// [6]: warp-level march iterations; [8..11]: by busy lanes (1-8, 9-16, 17-24, 25-32)
-			atomicAdd(&P.stats->dbg[6], 1ULL);
-			atomicAdd(&P.stats->dbg[8 + ((n_active - 1) >> 3)], 1ULL);
 		}
 	}
 }
