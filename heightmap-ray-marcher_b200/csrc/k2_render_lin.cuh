@@ -32,6 +32,11 @@
 //     binade-aware closed form (fact 1).  On the bench frames that happens 0 times; the model's periodic re-anchoring
 //     is its only regular caller.
 //
+// (Tried and measured in round 2, profiles/r02_kernel_experiments.txt: prefetching the level-0 texels of the next cell
+// tests, +1.5..24 % — the kernel is short of issue slots, not of memory parallelism; refilling idle lanes from a
+// per-warp stack of rays, k2_render_pack.cuh: 30 of 32 lanes busy instead of 24, but +27..57 % because refilled lanes
+// are at unrelated phases of their marches and every warp iteration then runs every path of this loop.)
+//
 // Rays whose per-step motion or start position does not fit the integer model (steps of thousands of cells, a
 // start 2^31 units away, NaNs, no lateral motion at all) take the plain per-step loop of the brute kernel.
 #ifndef HMRM_K2_RENDER_LIN_CUH
@@ -47,13 +52,6 @@ namespace hmrm {
 #endif
 #ifndef HMRM_LIN_CTAS
 #define HMRM_LIN_CTAS 4
-#endif
-
-#ifndef HMRM_EXP_PREFETCH
-#define HMRM_EXP_PREFETCH 0
-#endif
-#ifndef HMRM_EXP_PREFETCH_L2
-#define HMRM_EXP_PREFETCH_L2 0
 #endif
 
 #define HMRM_LIN_FRAC 16
@@ -175,23 +173,6 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		const unsigned idx = d.x + pyr_index<kLayout>((unsigned)(vx >> (k + lvl)), (unsigned)(vy >> (k + lvl)), d.y);
 		return (int)__ldg(P.lv + HMRM_CHECKED(P, idx, P.lv_total));
 	};
-	// Prefetch of the level-0 texel of sample j (no destination register, no scoreboard): a ray that has come down to
-	// cell tests usually needs the cells of its next samples too, one step apart — in different sectors of a plane no
-	// cache holds — and without this every one of those fetches is a full, serial DRAM round trip.
-	auto prefetch_cell = [&](unsigned j) {
-		const long long px_ = lin_acc(lx, j), py_ = lin_acc(ly, j);
-		const int ux = (int)(px_ >> HMRM_LIN_FRAC), uy = (int)(py_ >> HMRM_LIN_FRAC);
-		if (((unsigned)((unsigned long long)px_ >> 32) | (unsigned)((unsigned long long)py_ >> 32)) < 65536u &&
-		    (unsigned)ux < P.lin_grid_x && (unsigned)uy < P.lin_grid_y) {
-			const uint2 d = P.lv_desc[0];
-			const uint16_t *addr = P.lv + d.x + pyr_index<kLayout>((unsigned)(ux >> k), (unsigned)(uy >> k), d.y);
-#if HMRM_EXP_PREFETCH_L2
-			asm volatile("prefetch.global.L2 [%0];" ::"l"(addr));
-#else
-			asm volatile("prefetch.global.L1 [%0];" ::"l"(addr));
-#endif
-		}
-	};
 	// `above q` / `below q` with the model's error (< 1.6/16 Zq) and Zq16's rounding (ties at q +- 1/2) covered
 	auto above = [&](int vz, int q) -> bool { return vz > (q << 4) + HMRM_LIN_ZMARGIN && q < 65535; };
 
@@ -251,9 +232,6 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 		int q = 0;
 		if (!exact) {
 			// ---- A: find a level whose neighbourhood this sample clears (descend), or reach the cell itself ----
-#if HMRM_EXP_PREFETCH >= 3
-			if (level == P.lmin) prefetch_cell(j);      // speculative: a failed test at the lowest block level goes to the cell
-#endif
 			q = probe(level, vx, vy);
 			if (kStats) fetches += 1u;
 			while (!above(vz, q) && level > 0) {
@@ -262,12 +240,6 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 				if (kStats) { fetches += 1u; tally.dbg[3] += 1u; }
 			}
 			if (level == 0) {
-#if HMRM_EXP_PREFETCH >= 1
-				prefetch_cell(j + 1u);
-#endif
-#if HMRM_EXP_PREFETCH >= 2
-				prefetch_cell(j + 2u);
-#endif
 				const int fx = vx & cell_mask, fy = vy & cell_mask;
 				exact = fx < HMRM_LIN_MARGIN || fy < HMRM_LIN_MARGIN || fx > cell_mask - HMRM_LIN_MARGIN || fy > cell_mask - HMRM_LIN_MARGIN;
 			}

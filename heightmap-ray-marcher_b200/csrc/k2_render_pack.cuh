@@ -35,10 +35,13 @@ namespace hmrm {
 #ifndef HMRM_PACK_THRESH
 #define HMRM_PACK_THRESH 16
 #endif
-#define HMRM_PACK_QCAP 64          // records per warp: <= 31 (parked / left over) + 32 (one tile) at any time
+// Rays of one warp live in three places: its lanes, its stack, its notes.  A tile (<= 32 new rays) is only set up when
+// every ray of the warp is on the stack and there are fewer than 32 of them, so the warp never owns more than 63 rays:
+// neither the stack nor the list of notes can overflow.
+#define HMRM_PACK_QCAP 64          // records per warp
 #define HMRM_PACK_WORDS 16         // 32-bit words per record
 
-#define HMRM_PACK_SLOWCAP 32       // notes per warp: at most one per marching lane between two services
+#define HMRM_PACK_SLOWCAP 64       // notes per warp
 
 enum { kPackContinue = 0, kPackHit = 1, kPackMiss = 2, kPackCutOff = 3, kPackSlow = 4 };
 // reasons of a note (bits 8.. of its level word)
@@ -365,7 +368,7 @@ __device__ __noinline__ void pack_refill(const RenderParams &P, PackQueue Q, con
 	bool tiles_left = io[3] != 0u;
 	int notes = (int)io[4];
 
-	// `first` pass: the notes (at most 32, one per lane); then tiles
+	// first the notes, 32 at a time (one per lane); then tiles
 	for (;;) {
 		const bool serving = notes > 0;
 		if (!serving && !(count < 32 && tiles_left)) break;
@@ -375,16 +378,18 @@ __device__ __noinline__ void pack_refill(const RenderParams &P, PackQueue Q, con
 		int level = P.lstart;
 		int reason = 0;
 		if (serving) {
-			if (lane < notes) {
-				const unsigned pixel = S[0][lane];
+			const int take = min(notes, 32);
+			if (lane < take) {
+				const int at = notes - take + lane;
+				const unsigned pixel = S[0][at];
 				px = (int)(pixel & 0xFFFFu);
 				py = (int)(pixel >> 16);
-				at_n = S[1][lane];
-				reason = (int)S[2][lane] & ~0xFF;
-				level = (int)S[2][lane] & 0xFF;
+				at_n = S[1][at];
+				reason = (int)S[2][at] & ~0xFF;
+				level = (int)S[2][at] & 0xFF;
 				selected = true;
 			}
-			notes = 0;
+			notes -= take;
 		}
 		else {
 			if (cur == end) {
@@ -565,9 +570,8 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_PACK_CTAS) k2_render_pa
 			}
 			const int n_active = __popc(active);
 
-			// ---- back to the refill phase: when lanes would idle (or the notes could overflow), with every lane free ----
-			const bool want_refill = (count == 0 && n_active <= HMRM_PACK_THRESH && (tiles_left || notes > 0)) ||
-			                         notes + n_active > HMRM_PACK_SLOWCAP;
+			// ---- back to the refill phase: when lanes would idle, and with every lane free ----
+			const bool want_refill = count == 0 && n_active <= HMRM_PACK_THRESH && (tiles_left || notes > 0);
 			if (want_refill || n_active == 0) {
 				if (has) {                               // park: records are resumable
 					pack_put(Q, count + __popc(active & lt_mask), ray);
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_PACK_CTAS) k2_render_pa
 					has = false;
 				}
 			}
-			// rays that asked for the exact arithmetic leave a note (the SLOWCAP test above guarantees the room)
+			// rays that asked for the exact arithmetic leave a note
 			const unsigned sm = __ballot_sync(0xFFFFFFFFu, slow);
 			if (sm) {
 				if (slow) {
