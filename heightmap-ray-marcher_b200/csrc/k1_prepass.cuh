@@ -358,31 +358,27 @@ struct DilateJob {
 };
 
 __global__ void __launch_bounds__(256) k1_dilate_levels(const uint16_t *__restrict__ plain, uint16_t *__restrict__ pyr, DilateJob job) {
-	// Work item = a 4 x 4 block of outputs: six input rows (two of halo), one 8-byte load each, give the sixteen 3x3
-	// maxima; the two horizontal neighbours of every row come from the adjacent lanes (consecutive lanes own
-	// consecutive blocks of a row) by shuffle, from memory only at the ends of a warp or of a row.  In the tiled layouts
-	// the block is one 32-byte sector of the destination.
+	// Work item = a 4 x 4 block of outputs: six input rows (two of halo), each one 8-byte load plus its two horizontal
+	// neighbours, give the sixteen 3x3 maxima; in the tiled layouts the block is one 32-byte sector of the destination.
 	const unsigned long long total = job.first_item[job.n_levels];
 	const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-	const int lane = threadIdx.x & 31;
-	// (the loop bound is warp-uniform: every lane takes part in the shuffles, lanes past the end are masked)
-	for (unsigned long long item0 = (unsigned long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); item0 < total; item0 += stride) {
-		const unsigned long long item = item0 + (unsigned)lane;
-		const bool valid = item < total;
-		const unsigned long long it = valid ? item : total - 1ULL;
+	for (unsigned long long item = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; item < total; item += stride) {
 		int l = 1;
-		while (l + 1 < job.n_levels && it >= job.first_item[l + 1]) l += 1;
+		while (l + 1 < job.n_levels && item >= job.first_item[l + 1]) l += 1;
 		const int w = job.w[l], h = job.h[l];
 		const unsigned wq = (unsigned)(w + 3) / 4u;
-		const unsigned t = (unsigned)(it - job.first_item[l]);          // < 2^26 items per level
+		const unsigned t = (unsigned)(item - job.first_item[l]);          // < 2^26 items per level
 		const int xq = (int)(t % wq), yq = (int)(t / wq);
 		const int x = xq * 4, y = yq * 4;
 		const uint16_t *src = plain + job.plain_off[l];
 		const bool vec = (w & 3) == 0;
 		// All loads are issued unconditionally from clamped addresses and masked afterwards: with a branch per row the
-		// six rows were fetched one after the other (12 bytes in flight per thread, 1.8 TB/s).
+		// six rows were fetched one after the other (12 bytes in flight per thread, 1.8 TB/s); this way the eighteen
+		// loads of a block are independent.
 		unsigned hmax[6][4];           // per input row y-1 .. y+4: horizontal 3-max of the four columns
 		uint2 vrow[6];
+		unsigned lft[6], rgt[6];
+		const int xl = max(x - 1, 0), xr = min(x + 4, w - 1);
 #pragma unroll
 		for (int r = 0; r < 6; ++r) {
 			const int yy = min(max(y - 1 + r, 0), h - 1);
@@ -393,24 +389,15 @@ __global__ void __launch_bounds__(256) k1_dilate_levels(const uint16_t *__restri
 				const unsigned c2 = __ldg(row + min(x + 2, w - 1)), c3 = __ldg(row + min(x + 3, w - 1));
 				vrow[r] = make_uint2(c0 | (c1 << 16), c2 | (c3 << 16));
 			}
+			lft[r] = __ldg(row + xl);
+			rgt[r] = __ldg(row + xr);
 		}
-		// the neighbouring lanes hold the neighbouring blocks of the same row iff they are on the same level and this
-		// block is not the first / last of its row
-		const int l_prev = __shfl_up_sync(0xFFFFFFFFu, l, 1), l_next = __shfl_down_sync(0xFFFFFFFFu, l, 1);
-		const bool prev_valid = __shfl_up_sync(0xFFFFFFFFu, valid ? 1 : 0, 1) != 0;
-		const bool next_valid = __shfl_down_sync(0xFFFFFFFFu, valid ? 1 : 0, 1) != 0;
-		const bool left_by_shfl = lane > 0 && prev_valid && l_prev == l && xq > 0;
-		const bool right_by_shfl = lane < 31 && next_valid && l_next == l && xq + 1 < (int)wq;
-		const int xl = max(x - 1, 0), xr = min(x + 4, w - 1);
 #pragma unroll
 		for (int r = 0; r < 6; ++r) {
 			const int yy = y - 1 + r;
 			const bool row_in = yy >= 0 && yy < h;
 			unsigned c0 = vrow[r].x & 0xFFFFu, c1 = vrow[r].x >> 16, c2 = vrow[r].y & 0xFFFFu, c3 = vrow[r].y >> 16;
-			unsigned l_ = __shfl_up_sync(0xFFFFFFFFu, c3, 1), r_ = __shfl_down_sync(0xFFFFFFFFu, c0, 1);
-			const uint16_t *row = src + (size_t)min(max(yy, 0), h - 1) * w;
-			if (!left_by_shfl) l_ = __ldg(row + xl);
-			if (!right_by_shfl) r_ = __ldg(row + xr);
+			unsigned l_ = lft[r], r_ = rgt[r];
 			// texels outside the level count as 0 (heights are unsigned)
 			if (!row_in) c0 = c1 = c2 = c3 = l_ = r_ = 0u;
 			if (x + 1 >= w) c1 = 0u;
@@ -423,7 +410,6 @@ __global__ void __launch_bounds__(256) k1_dilate_levels(const uint16_t *__restri
 			hmax[r][2] = max(c1, max(c2, c3));
 			hmax[r][3] = max(c2, max(c3, r_));
 		}
-		if (!valid) continue;
 		uint16_t *dst = pyr + job.dst_off[l];
 		uint2 rows[4];
 #pragma unroll

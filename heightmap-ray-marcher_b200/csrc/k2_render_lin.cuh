@@ -115,15 +115,11 @@ __device__ __forceinline__ bool lin_slope(double s_units, long long &d) {
 	return true;
 }
 
-// The reference's exact FP64 sample n of pixel (px, py), rebuilt from the pixel: out[0..2] = position, out[3..5] =
-// per-step addend (main/hmap.cpp:985-998, :1037).  The march keeps NO exact state of its own: the few samples that need
-// it (model re-anchoring every 65536 samples, samples the model cannot decide, rays outside the model) pay for the ray
-// set-up again here instead of every ray keeping twelve doubles on the stack through the whole loop (round 1: 12.5 M
-// sectors of local-memory stores per 4K frame).
-__device__ __noinline__ void lin_exact_sample(const RenderParams &P, int px, int py, unsigned n, double out[6]) {
-	const Ray ray = generate_ray(P, px, py);
-	double ex = 0.0, ey = 0.0, ez = 0.0, dist;
-	box_entry_at(P.c0, P.c1, ray, ex, ey, ez, dist);      // (the ray is being marched: it entered)
+template <bool kStats, int kLayout>
+__device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray, double ex, double ey, double ez,
+                                          unsigned &hit_cell, bool &real_hit, int &first_hit, PixelTally &tally) {
+	const int k = P.fx_bits;
+	// exact state: the anchor sample and the reference's per-step addend
 	AxisState ax, ay, az;
 	ax.p = fadd(ex, fmul(P.nudge, ray.dx));           // main/hmap.cpp:998
 	ay.p = fadd(ey, fmul(P.nudge, ray.dy));
@@ -133,23 +129,7 @@ __device__ __noinline__ void lin_exact_sample(const RenderParams &P, int px, int
 	az.s = fmul(P.step_dist, ray.dz);
 	ax.tag = ay.tag = az.tag = INT_MIN;
 	ax.S = ay.S = az.S = 0.0;
-	unsigned a = 0u;
-	advance_exact(ax, ay, az, a, n);
-	out[0] = ax.p; out[1] = ay.p; out[2] = az.p;
-	out[3] = ax.s; out[4] = ay.s; out[5] = az.s;
-}
-
-template <bool kStats, int kLayout>
-__device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray, double ex, double ey, double ez, int px, int py,
-                                          unsigned &hit_cell, bool &real_hit, int &first_hit, PixelTally &tally) {
-	const int k = P.fx_bits;
-	// exact start of the march and the reference's per-step addend: used for the model below, then dead
-	const double p0x = fadd(ex, fmul(P.nudge, ray.dx));           // main/hmap.cpp:998
-	const double p0y = fadd(ey, fmul(P.nudge, ray.dy));
-	const double p0z = fadd(ez, fmul(P.nudge, ray.dz));
-	const double s0x = fmul(P.step_dist, ray.dx);                  // :1037
-	const double s0y = fmul(P.step_dist, ray.dy);
-	const double s0z = fmul(P.step_dist, ray.dz);
+	unsigned anchor = 0u;     // sample index of (ax.p, ay.p, az.p)
 
 	unsigned n = 0u;          // sample under examination
 	unsigned fetches = 0u;
@@ -161,22 +141,22 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 	const double zc = P.zq_offset - HMRM_MAGIC;
 	const double zs16 = P.zq_scale * 16.0, zo16 = __fma_rn(16.0, zc, HMRM_MAGIC);
 	LinAxis lx, ly, lz;
-	bool model = lin_slope(s0x * P.fx_scale, lx.d) && lin_slope(-s0y * P.fx_scale, ly.d) && lin_slope(s0z * zs16, lz.d);
+	bool model = lin_slope(ax.s * P.fx_scale, lx.d) && lin_slope(-ay.s * P.fx_scale, ly.d) && lin_slope(az.s * zs16, lz.d);
 	model = model && fabs(zc) < 1.0e12;
 	// no lateral motion and not coming down: such a ray can only end by the reference's hang; the per-step loop cuts it
 	model = model && (lx.d != 0 || ly.d != 0 || lz.d < 0);
-	auto rebase = [&](double x, double y, double z) -> bool {     // V_0 of the model := this exact position
+	auto rebase = [&]() -> bool {                     // V_0 of the model := the exact anchor
 		int vx, vy, vz;
-		const bool okx = magic_decode(__fma_rn(x, P.fx_scale, HMRM_MAGIC), vx);
-		const bool oky = magic_decode(__fma_rn(y, -P.fx_scale, HMRM_MAGIC), vy);
-		const bool okz = magic_decode(__fma_rn(z, zs16, zo16), vz);
+		const bool okx = magic_decode(__fma_rn(ax.p, P.fx_scale, HMRM_MAGIC), vx);
+		const bool oky = magic_decode(__fma_rn(ay.p, -P.fx_scale, HMRM_MAGIC), vy);
+		const bool okz = magic_decode(__fma_rn(az.p, zs16, zo16), vz);
 		lx.a0 = ((long long)vx << HMRM_LIN_FRAC) + (1LL << (HMRM_LIN_FRAC - 1));
 		ly.a0 = ((long long)vy << HMRM_LIN_FRAC) + (1LL << (HMRM_LIN_FRAC - 1));
 		lz.a0 = ((long long)vz << HMRM_LIN_FRAC) + (1LL << (HMRM_LIN_FRAC - 1));
 		return okx && oky && okz;
 	};
 	unsigned base = 0u;       // sample index of V_0
-	model = model && rebase(p0x, p0y, p0z);
+	model = model && rebase();
 
 	bool finished = false;     // the integer-model loop reached a verdict
 	if (model) {
@@ -207,10 +187,9 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 				finished = true;
 				break;
 			}
-			double e[6];
-			lin_exact_sample(P, px, py, n, e);
+			advance_exact(ax, ay, az, anchor, n);
 			base = n;
-			if (!rebase(e[0], e[1], e[2])) {   // left the representable range: finish with the per-step loop below
+			if (!rebase()) {                 // left the representable range: finish with the per-step loop below
 				model = false;
 				break;
 			}
@@ -325,13 +304,11 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			// z < surf (main/hmap.cpp:1001-1016) — are decided unless the sample is within ~1e-12 of a cell edge or of the
 			// surface.  This settles the (-1, 0) truncation strip, cell and grid edges, clamped 16-bit heights and ties.
 			{
-				double e0[6];                   // exact sample 0 and the addend, rebuilt from the pixel
-				lin_exact_sample(P, px, py, 0u, e0);
-				const double mj = (double)n;
+				const double mj = (double)(n - anchor);
 				const double rel = fmul(fadd(mj, 2.0), 2.3e-16);
-				const double xe = __fma_rn(mj, e0[3], e0[0]), ye = __fma_rn(mj, e0[4], e0[1]), ze = __fma_rn(mj, e0[5], e0[2]);
-				const double bx = fmul(rel, fmax(fabs(e0[0]), fabs(xe))), by = fmul(rel, fmax(fabs(e0[1]), fabs(ye)));
-				const double bz = fmul(rel, fmax(fabs(e0[2]), fabs(ze)));
+				const double xe = __fma_rn(mj, ax.s, ax.p), ye = __fma_rn(mj, ay.s, ay.p), ze = __fma_rn(mj, az.s, az.p);
+				const double bx = fmul(rel, fmax(fabs(ax.p), fabs(xe))), by = fmul(rel, fmax(fabs(ay.p), fabs(ye)));
+				const double bz = fmul(rel, fmax(fabs(az.p), fabs(ze)));
 				const double qx = fdiv(xe, P.gw), qy = fdiv(-ye, P.gw);
 				// fl(x_true / gw) differs from qx by at most bx / gw + 2^-52 |q|; (int) truncates toward zero, so the only
 				// break points are the non-zero integers
@@ -367,16 +344,15 @@ __device__ __forceinline__ void march_lin(const RenderParams &P, const Ray &ray,
 			}
 			// still undecided: reconstruct the exact sample and let the reference's own expressions decide
 			if (kStats) tally.dbg[7] += 1u;
-			double en[6];
-			lin_exact_sample(P, px, py, n, en);
-			const int gx = trunc_cell(fdiv(en[0], P.gw)), gy = trunc_cell(fdiv(-en[1], P.gw));
+			advance_exact(ax, ay, az, anchor, n);
+			const int gx = trunc_cell(fdiv(ax.p, P.gw)), gy = trunc_cell(fdiv(-ay.p, P.gw));
 			if (gx < 0 || gy < 0 || gx >= P.map_w || gy >= P.map_h) {
 				finished = true;
 				break;
 			}
 			const size_t cell = (size_t)gx + (size_t)gy * (size_t)P.map_w;
 			if (kStats) fetches += 1u;
-			if (en[2] < __ldg(P.surf + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h))) {
+			if (az.p < __ldg(P.surf + HMRM_CHECKED(P, cell, (size_t)P.map_w * (size_t)P.map_h))) {
 				hit_cell = (unsigned)cell;      // colour fetched by the caller, once the whole warp is out of the loop
 				real_hit = true;
 				first_hit = (n > 0x7FFFFFFFu) ? 0x7FFFFFFF : (int)n;
@@ -398,11 +374,7 @@ next_sample:
 	if (!finished) {
 		// The plain per-step loop (k2_render_brute.cuh) from the exact anchor on, with a cap instead of a hang: rays
 		// that do not fit the integer model, and rays that left its representable range.
-		double e[6];
-		lin_exact_sample(P, px, py, n, e);
-		AxisState ax, ay, az;
-		ax.p = e[0]; ay.p = e[1]; az.p = e[2];
-		ax.s = e[3]; ay.s = e[4]; az.s = e[5];
+		advance_exact(ax, ay, az, anchor, n);
 		unsigned long long kk = n;
 		for (;;) {
 			const int gx = trunc_cell(fdiv(ax.p, P.gw)), gy = trunc_cell(fdiv(-ay.p, P.gw));
@@ -476,7 +448,7 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin
 			if (entered) {
 				tally.box_hit = 1u;
 				first_hit = -2;
-				march_lin<kStats, kLayout>(P, ray, ex, ey, ez, px, py, hit_cell, real_hit, first_hit, tally);
+				march_lin<kStats, kLayout>(P, ray, ex, ey, ez, hit_cell, real_hit, first_hit, tally);
 			}
 			if (!real_hit) rgba = miss_colour(P, ray.dz);
 			else {
