@@ -267,9 +267,10 @@ class Job:
         self.d_out = torch.zeros((MG.padded_height(self.H), self.W, 4), dtype=torch.uint8, device=f"cuda:{local}")
         self.peer = None
         self.band_i = 0
-        if self.bands and world > 1 and args.exchange in ("peer", "peer-allreduce"):
+        if self.bands and world > 1 and args.exchange in ("peer", "peer-copy", "peer-allreduce"):
             self.peer = MG.PeerFrame(self.r, self.H, self.W, rank, world, local, channels=self.channels,
-                                     completion="device" if args.exchange == "peer" else "allreduce")
+                                     completion="allreduce" if args.exchange == "peer-allreduce" else "device",
+                                     exchange="copy" if args.exchange == "peer-copy" else "stores")
 
     def frame_of(self, n: int, flags: int = 0, w: int = 0, h: int = 0, whole: bool = False, fmt=None):
         w, h = w or self.W, h or self.H
@@ -552,6 +553,10 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
                                     + {"peer": "every rank's kernel stores its bands straight into rank 0's frame (CUDA IPC peer "
                                                "memory over NVLink); completion and buffer release through device-side counters "
                                                "in rank 0's memory (no collective)",
+                                       "peer-copy": "every rank renders its bands into a staging frame on its own device and pushes "
+                                                    "its tile rows into rank 0's frame with one strided device-to-device copy "
+                                                    "(CUDA IPC peer memory over NVLink, copy engine); completion and buffer "
+                                                    "release through device-side counters in rank 0's memory (no collective)",
                                        "peer-allreduce": "every rank's kernel stores its bands straight into rank 0's frame; "
                                                          "one-element NCCL all-reduce as the completion barrier",
                                        "gather": "bands packed, gathered to rank 0 (NCCL), unpacked"}[args.exchange]
@@ -731,7 +736,7 @@ def main() -> None:
                     help="frame format: rgb8 = the reference's pixels without the constant alpha byte (default), "
                          "rgba8 = the reference's framebuf layout")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", choices=["peer", "peer-allreduce", "gather"], default="peer",
+    ap.add_argument("--exchange", choices=["peer", "peer-copy", "peer-allreduce", "gather"], default="peer",
                     help="bands workloads at N > 1: how the bands reach rank 0")
     ap.add_argument("--no-bands", action="store_true", help="N > 1: skip the bands8k sub-record")
     ap.add_argument("--bands-workload", choices=["bands8k", "smokebands"], default="bands8k")

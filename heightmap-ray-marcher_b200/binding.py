@@ -113,6 +113,8 @@ PROTOTYPES = {
     "hmrm_ipc_open": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "hmrm_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hmrm_render_peer": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "hmrm_render_peer_staged": (C.c_int, [C.c_void_p, C.POINTER(Frame), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                          C.c_void_p]),
     "hmrm_peer_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]),
     "hmrm_peer_release": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "hmrm_peer_status": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
@@ -368,6 +370,10 @@ class Renderer:
     def render_peer(self, frame: Frame, d_frame: int, d_ctrl: int, use: int, stream=None) -> None:
         self._check(self._lib.hmrm_render_peer(self._h, C.byref(frame), C.c_void_p(d_frame), C.c_void_p(d_ctrl), use,
                                                _ptr(stream)))
+
+    def render_peer_staged(self, frame: Frame, d_stage, d_frame: int, d_ctrl: int, use: int, stream=None) -> None:
+        self._check(self._lib.hmrm_render_peer_staged(self._h, C.byref(frame), _ptr(d_stage), C.c_void_p(d_frame),
+                                                      C.c_void_p(d_ctrl), use, _ptr(stream)))
 
     def peer_wait(self, d_ctrl: int, use: int, ranks: int, stream=None) -> None:
         self._check(self._lib.hmrm_peer_wait(self._h, C.c_void_p(d_ctrl), use, ranks, _ptr(stream)))

@@ -630,7 +630,9 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 // D2H of what one launch rendered: rows [rb, re), or with band_count > 1 only the tile rows of that band (several
 // ranks may fill one shared, registered host frame, each over its own PCIe link): one strided copy + the ragged last
 // tile row.  Enqueued on the copy stream.
-int enqueue_copy_out(hmrm_ctx *c, const hmrm_frame *f, const uint32_t *fb, uint8_t *rgba_out, int rb, int re) {
+int enqueue_copy_out(hmrm_ctx *c, const hmrm_frame *f, const uint32_t *fb, uint8_t *rgba_out, int rb, int re,
+                     cudaMemcpyKind kind = cudaMemcpyDeviceToHost, cudaStream_t on = NULL) {
+	const cudaStream_t copy_stream = on ? on : c->copy_stream;
 	const size_t row_bytes = (size_t)f->screen_width * (f->pixel_format == HMRM_PIXEL_RGB8 ? 3 : 4);
 	if (f->band_count > 1) {
 		const int tile_rows = (re - rb + 3) / 4;
@@ -643,17 +645,17 @@ int enqueue_copy_out(hmrm_ctx *c, const hmrm_frame *f, const uint32_t *fb, uint8
 			const size_t pitch = (size_t)f->band_count * 4 * row_bytes;
 			if (full > 0)
 				HMRM_CUDA(c, cudaMemcpy2DAsync(rgba_out + first, pitch, (const uint8_t *)fb + first, pitch, 4 * row_bytes,
-				                               (size_t)full, cudaMemcpyDeviceToHost, c->copy_stream));
+				                               (size_t)full, kind, copy_stream));
 			if (full < owned) {
 				const size_t at = (size_t)(rb + last_tile * 4) * row_bytes;
-				HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + at, (const uint8_t *)fb + at, (size_t)last_rows * row_bytes,
-				                             cudaMemcpyDeviceToHost, c->copy_stream));
+				HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + at, (const uint8_t *)fb + at, (size_t)last_rows * row_bytes, kind,
+				                             copy_stream));
 			}
 		}
 	}
 	else {
 		HMRM_CUDA(c, cudaMemcpyAsync(rgba_out + (size_t)rb * row_bytes, (const uint8_t *)fb + (size_t)rb * row_bytes,
-		                             (size_t)(re - rb) * row_bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+		                             (size_t)(re - rb) * row_bytes, kind, copy_stream));
 	}
 	return HMRM_OK;
 }
@@ -1302,6 +1304,29 @@ int hmrm_render_peer(hmrm_ctx *c, const hmrm_frame *f, void *d_frame, void *d_ct
 	k_peer_spin<<<1, 1, 0, s>>>(&ctrl->released, use - 1u, &ctrl->error, c->knobs.peer_timeout_ns);
 	HMRM_CUDA(c, cudaGetLastError());
 	const int rc = enqueue_render(c, f, (uint32_t *)d_frame, s, true);
+	if (rc) return rc;
+	k_peer_signal<<<1, 1, 0, s>>>(&ctrl->arrived);
+	HMRM_CUDA(c, cudaGetLastError());
+	return HMRM_OK;
+}
+
+int hmrm_render_peer_staged(hmrm_ctx *c, const hmrm_frame *f, void *d_stage, void *d_frame, void *d_ctrl, uint32_t use,
+                            void *stream) {
+	if (!c) return HMRM_ERR_INVALID;
+	if (!d_stage || !d_frame || !d_ctrl || use == 0u) return fail(c, HMRM_ERR_INVALID, "hmrm_render_peer_staged: bad arguments");
+	HMRM_CUDA(c, cudaSetDevice(c->device));
+	cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+	PeerCtrl *ctrl = (PeerCtrl *)d_ctrl;
+	// render into this device's own staging frame (ordinary stores), ...
+	int rc = enqueue_render(c, f, (uint32_t *)d_stage, s, true);
+	if (rc) return rc;
+	// ... then, once the root has read the previous use of the shared buffer, push this rank's tile rows over NVLink
+	// with the copy engine: large transfers instead of the kernel's 24- or 32-byte row pieces
+	k_peer_spin<<<1, 1, 0, s>>>(&ctrl->released, use - 1u, &ctrl->error, c->knobs.peer_timeout_ns);
+	HMRM_CUDA(c, cudaGetLastError());
+	int rb = f->row_begin, re = f->row_end;
+	if (rb == 0 && re == 0) re = f->screen_height;
+	rc = enqueue_copy_out(c, f, (const uint32_t *)d_stage, (uint8_t *)d_frame, rb, re, cudaMemcpyDeviceToDevice, s);
 	if (rc) return rc;
 	k_peer_signal<<<1, 1, 0, s>>>(&ctrl->arrived);
 	HMRM_CUDA(c, cudaGetLastError());

@@ -97,6 +97,11 @@ class PeerFrame:
     frames").  Replaces pack -> NCCL gather -> unpack of `gather_interleaved_bands`: the exchange is fused into the
     render kernel's own pixel stores.
 
+    exchange = "stores" (default): the render kernel's own pixel stores go to the root's memory.  exchange = "copy": every
+    non-root rank renders into a staging frame on its own device and pushes its tile rows with one strided
+    device-to-device copy (large NVLink transfers; wins when many ranks write into one root).  The root always renders
+    straight into its own frame.
+
     completion = "device" (default): the ranks tell the root "my bands are in" through a counter in the root's memory
     and the root tells them "buffer read" through another (csrc/peer_sync.cuh) — stream-ordered one-thread kernels, no
     collective, no host synchronisation.  completion = "allreduce": round 1's one-element all-reduce as the barrier
@@ -110,11 +115,13 @@ class PeerFrame:
     """
 
     def __init__(self, renderer, height: int, width: int, rank: int, world: int, device: int, root: int = 0,
-                 buffers: int = 2, group=None, channels: int = 4, completion: str = "device"):
+                 buffers: int = 2, group=None, channels: int = 4, completion: str = "device", exchange: str = "stores"):
         import torch
         import torch.distributed as dist
 
-        assert channels in (3, 4) and completion in ("device", "allreduce")
+        assert channels in (3, 4) and completion in ("device", "allreduce") and exchange in ("stores", "copy")
+        assert exchange == "stores" or completion == "device"
+        self.exchange = exchange
         self.r, self.height, self.width, self.channels = renderer, height, width, channels
         self.rank, self.world, self.root, self.group, self.device = rank, world, root, group, device
         self.completion = completion
@@ -138,6 +145,9 @@ class PeerFrame:
                 p = renderer.ipc_open(bytes(handle.cpu().tolist()))
             self.ptrs.append(p)
         self.token = torch.zeros(1, dtype=torch.float32, device=where)
+        self.stage = None
+        if exchange == "copy" and rank != root:
+            self.stage = [torch.zeros(self.frame_bytes, dtype=torch.uint8, device=f"cuda:{device}") for _ in range(buffers)]
 
     def pointer(self, i: int) -> int:
         """Device pointer (valid in THIS process) of buffer i mod buffers."""
@@ -151,7 +161,9 @@ class PeerFrame:
 
     def render(self, frame, i: int, stream=None) -> None:
         """This rank's bands of frame i into the root's buffer (asynchronous, on `stream`)."""
-        if self.completion == "device":
+        if self.stage is not None:
+            self.r.render_peer_staged(frame, self.stage[i % len(self.stage)], self.pointer(i), self.ctrl(i), self.use(i), stream)
+        elif self.completion == "device":
             self.r.render_peer(frame, self.pointer(i), self.ctrl(i), self.use(i), stream)
         else:
             self.r.render_device(frame, self.pointer(i), stream)

@@ -217,6 +217,12 @@ int hmrm_ipc_close(hmrm_ctx *ctx, void *dptr);
  * hmrm_peer_status returns {arrived, released, error}. */
 #define HMRM_PEER_CTRL_BYTES 256
 int hmrm_render_peer(hmrm_ctx *ctx, const hmrm_frame *f, void *d_frame, void *d_ctrl, uint32_t use, void *stream);
+/* The same with the exchange done by the copy engine: the rank renders its bands into d_stage (a frame-sized buffer
+ * on ITS device), then pushes exactly its tile rows into d_frame with one strided device-to-device copy, then counts
+ * itself in.  One more pass over the rank's rows, but NVLink sees large transfers instead of the kernel's 24- / 32-byte
+ * row pieces: the faster exchange when many ranks write into one root. */
+int hmrm_render_peer_staged(hmrm_ctx *ctx, const hmrm_frame *f, void *d_stage, void *d_frame, void *d_ctrl, uint32_t use,
+                            void *stream);
 int hmrm_peer_wait(hmrm_ctx *ctx, void *d_ctrl, uint32_t use, int32_t ranks, void *stream);
 int hmrm_peer_release(hmrm_ctx *ctx, void *d_ctrl, uint32_t use, void *stream);
 int hmrm_peer_status(hmrm_ctx *ctx, void *d_ctrl, uint32_t out[3]);

@@ -63,13 +63,19 @@ def test_device_side_completion_protocol_in_one_stream(hmrm):
         for channels in (4, 3):
             fmt = hmrm.PIXEL_RGB8 if channels == 3 else hmrm.PIXEL_RGBA8
             pf = MG.PeerFrame(r, H, W, 0, 1, 0, channels=channels, completion="device")
+            stage = torch.zeros(pf.frame_bytes, dtype=torch.uint8, device="cuda:0")
             for i in range(6):
                 common = dict(projection=1 + i % 3, screen_width=W, screen_height=H, cam_pos=(-3.0 + i, 3.0, 14.0 + i),
                               hang=hmrm.deg2rad(-45.0), vang=hmrm.deg2rad(112.0), hfov=hmrm.deg2rad(90.0), ortho_width=0.04,
                               grid_width=0.01, step_dist=0.05)
                 for rk in (2, 0, 1):         # any order: each call waits for the release of the previous use only
-                    r.render_peer(r.frame(band_count=ranks, band_index=rk, pixel_format=fmt, **common), pf.pointer(i),
-                                  pf.ctrl(i), pf.use(i), stream.cuda_stream)
+                    fr = r.frame(band_count=ranks, band_index=rk, pixel_format=fmt, **common)
+                    if rk == 1:
+                        # this "rank" exchanges through the copy engine: renders into its own staging frame, then pushes
+                        # its tile rows with one strided device-to-device copy (hmrm_render_peer_staged)
+                        r.render_peer_staged(fr, stage, pf.pointer(i), pf.ctrl(i), pf.use(i), stream.cuda_stream)
+                    else:
+                        r.render_peer(fr, pf.pointer(i), pf.ctrl(i), pf.use(i), stream.cuda_stream)
                 r.peer_wait(pf.ctrl(i), pf.use(i), ranks, stream.cuda_stream)
                 got = pf.tensor(i).cpu().numpy()
                 r.peer_release(pf.ctrl(i), pf.use(i), stream.cuda_stream)
