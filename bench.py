@@ -269,6 +269,7 @@ class Job:
         self.band_i = 0
         if self.bands and world > 1 and args.exchange in ("peer", "peer-copy", "peer-allreduce"):
             self.peer = MG.PeerFrame(self.r, self.H, self.W, rank, world, local, channels=self.channels,
+                                     buffers=max(2, min(4, args.inflight)),
                                      completion="allreduce" if args.exchange == "peer-allreduce" else "device",
                                      exchange="copy" if args.exchange == "peer-copy" else "stores")
 
@@ -373,7 +374,7 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
     if bands and job.peer is None:
         n_flight = 1                         # the NCCL gather path works on one buffer
     if job.peer is not None:
-        n_flight = min(n_flight, 2)          # PeerFrame rotates two buffers
+        n_flight = min(n_flight, len(job.peer.ptrs))     # one stream per rotating buffer
     streams = [stream] + [torch.cuda.Stream(device=local) for _ in range(n_flight - 1)]
     outs = [job.d_out] + [torch.zeros_like(job.d_out) for _ in range(n_flight - 1)]
     timed_frames = [job.frame_of(n) for n in my_frames]     # host-side frame descriptions, built outside the timed region
