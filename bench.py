@@ -267,9 +267,13 @@ class Job:
         self.d_out = torch.zeros((MG.padded_height(self.H), self.W, 4), dtype=torch.uint8, device=f"cuda:{local}")
         self.peer = None
         self.band_i = 0
+        if args.exchange == "auto":
+            # measured: the kernel's own peer stores win with one writer into the root (N = 2); with
+            # more writers their 24- / 32-byte row pieces saturate the root's NVLink ingress and the copy engine wins
+            args.exchange = "peer" if world <= 2 else "peer-copy"
         if self.bands and world > 1 and args.exchange in ("peer", "peer-copy", "peer-allreduce"):
             self.peer = MG.PeerFrame(self.r, self.H, self.W, rank, world, local, channels=self.channels,
-                                     buffers=max(2, min(4, args.inflight)),
+                                     buffers=max(2, min(4, args.bands_inflight)),
                                      completion="allreduce" if args.exchange == "peer-allreduce" else "device",
                                      exchange="copy" if args.exchange == "peer-copy" else "stores")
 
@@ -370,7 +374,7 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
     # Two frames in flight: frames alternate between two streams (and two output buffers) so that the next frame's
     # CTAs fill the SMs that the previous frame's tail leaves idle.  The timed region starts on `stream` with both
     # streams idle and ends on `stream` after it has joined the others.
-    n_flight = max(1, min(4, args.inflight))
+    n_flight = max(1, min(4, args.bands_inflight if bands else args.inflight))
     if bands and job.peer is None:
         n_flight = 1                         # the NCCL gather path works on one buffer
     if job.peer is not None:
@@ -737,13 +741,16 @@ def main() -> None:
                     help="frame format: rgb8 = the reference's pixels without the constant alpha byte (default), "
                          "rgba8 = the reference's framebuf layout")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", choices=["peer", "peer-copy", "peer-allreduce", "gather"], default="peer",
+    ap.add_argument("--exchange", choices=["auto", "peer", "peer-copy", "peer-allreduce", "gather"], default="auto",
                     help="bands workloads at N > 1: how the bands reach rank 0")
     ap.add_argument("--no-bands", action="store_true", help="N > 1: skip the bands8k sub-record")
     ap.add_argument("--bands-workload", choices=["bands8k", "smokebands"], default="bands8k")
     ap.add_argument("--bands-steps", type=int, default=96)
     ap.add_argument("--cpu-frames", type=int, default=2)
     ap.add_argument("--inflight", type=int, default=2, help="frames in flight in the device-resident timing (1..4)")
+    ap.add_argument("--bands-inflight", type=int, default=3,
+                    help="bands workloads: frames in flight (1..4; one stream and one peer buffer each); measured at N = 4: "
+                         "0.442 ms per 8K frame with 2, 0.411 ms with 3")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
