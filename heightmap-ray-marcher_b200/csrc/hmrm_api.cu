@@ -64,7 +64,7 @@ struct LaunchSlot {
 // scheduled / how many fetches are issued.
 struct Knobs {
 	bool no_row_order, no_batch, debug_sched;
-	int lmin_bias, lstride, lstart;
+	int lmin_bias, lstride, lstart, sky_batch;
 	float cell_exit, climb;
 	bool zq_shrink_set;
 	double zq_shrink;
@@ -420,6 +420,7 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	// camera position or heading, so a flythrough computes it once.
 	P.row_order = NULL;
 	P.batch_from_tile = 0xFFFFFFFFu;
+	P.sky_batch = (unsigned)c->knobs.sky_batch;
 	if (f->projection != HMRM_ORTHOGRAPHIC && P.tiles_y > 1 && !c->knobs.no_row_order) {
 		const double key[8] = {(double)f->projection, (double)W, (double)H, f->vang, f->hfov, (double)row_begin,
 		                       (double)(P.tile_y_first * 65536 + P.tile_y_step), (double)P.tiles_y};
@@ -706,6 +707,8 @@ int hmrm_create(int device, hmrm_ctx **out) {
 		k.lmin_bias = (e = std::getenv("HMRM_LMIN_BIAS")) ? std::atoi(e) : 0;
 		k.lstride = (e = std::getenv("HMRM_LSTRIDE")) ? std::atoi(e) : 1;
 		k.lstart = (e = std::getenv("HMRM_LSTART")) ? std::atoi(e) : 6;
+		k.sky_batch = (e = std::getenv("HMRM_SKY_BATCH")) ? std::atoi(e) : 8;
+		if (k.sky_batch < 1) k.sky_batch = 1;
 		k.cell_exit = (e = std::getenv("HMRM_CELL_EXIT")) ? (float)std::atof(e) : 8.0f;
 		k.climb = (e = std::getenv("HMRM_CLIMB")) ? (float)std::atof(e) : 4.0f;
 		k.zq_shrink_set = (e = std::getenv("HMRM_ZQ_RANGE_SHRINK")) != NULL;

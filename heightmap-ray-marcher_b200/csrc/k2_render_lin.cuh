@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(HMRM_LIN_THREADS, HMRM_LIN_CTAS) k2_render_lin
 	unsigned cur = 0u, end = 0u;
 	for (;;) {
 		if (cur == end) {
-			const unsigned batch = (end != 0u && end >= P.batch_from_tile) ? 8u : 1u;
+			const unsigned batch = (end != 0u && end >= P.batch_from_tile) ? P.sky_batch : 1u;
 			unsigned t = 0u;
 			if (lane == 0) t = atomicAdd(P.tile_counter, batch);
 			cur = __shfl_sync(0xFFFFFFFFu, t, 0);

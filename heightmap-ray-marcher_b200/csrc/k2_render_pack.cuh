@@ -395,7 +395,7 @@ __device__ __noinline__ void pack_refill(const RenderParams &P, PackQueue Q, con
 			if (cur == end) {
 				// (marching tiles are grabbed one at a time, the sky rows at the end of the schedule 8 at a time:
 				// k2_render_lin.cuh)
-				const unsigned batch = (end != 0u && end >= P.batch_from_tile) ? 8u : 1u;
+				const unsigned batch = (end != 0u && end >= P.batch_from_tile) ? P.sky_batch : 1u;
 				unsigned t = 0u;
 				if (lane == 0) t = atomicAdd(P.tile_counter, batch);
 				cur = __shfl_sync(0xFFFFFFFFu, t, 0);

@@ -30,7 +30,8 @@ struct RenderParams {
 	float inv_tiles_x;             // slightly less than 1 / tiles_x: tile -> (row, column) without an integer divide
 	int tile_y_first, tile_y_step; // launch tile row t is frame tile row tile_y_first + t * tile_y_step (row interleave)
 	const int *row_order;          // optional permutation of the launch tile rows: expensive (grazing) rows first
-	unsigned batch_from_tile;      // tiles from this queue position on look above the horizon: grabbed 8 at a time
+	unsigned batch_from_tile;      // tiles from this queue position on look above the horizon: grabbed sky_batch at a time
+	unsigned sky_batch;
 	// k2_render_lin: grid extents in fixed-point units (map << fx_bits, <= 2^30) and the same minus twice the margin;
 	// host-computed so that the march loop reads them as constant-bank operands
 	unsigned lin_grid_x, lin_grid_y, lin_span_x, lin_span_y;
