@@ -288,7 +288,7 @@ class Job:
                             pixel_format=self.fmt if fmt is None else fmt,
                             band_count=self.world if split else 0, band_index=self.rank if split else 0)
 
-    def render_step(self, n: int, flags: int = 0, stream=None, frame=None):
+    def render_step(self, n: int, flags: int = 0, stream=None, frame=None, out=None, want_tensor=False):
         """One step of the workload on this rank: a whole frame, or this rank's bands of the frame everybody works
         on.  Bands land in rank 0's frame by peer stores from the render kernel itself (default; completion on the
         device or by an all-reduce) or by pack + NCCL gather + unpack (--exchange gather)."""
@@ -299,12 +299,15 @@ class Job:
             i = self.band_i
             self.band_i += 1
             self.peer.render(frame, i, s.cuda_stream)
-            with self.torch.cuda.stream(s):
+            if self.peer.completion == "device":
                 self.peer.complete(i, s.cuda_stream)
+            else:
+                with self.torch.cuda.stream(s):
+                    self.peer.complete(i, s.cuda_stream)
             self.peer.release(i, s.cuda_stream)          # nothing reads the frame in the device-resident timing
-            return self.peer.tensor(i)
-        self.r.render_device(frame, self.d_out, s.cuda_stream)
-        if self.bands and self.world > 1:
+            return self.peer.tensor(i) if want_tensor else None
+        self.r.render_device(frame, self.d_out if out is None else out, s.cuda_stream)
+        if self.bands and self.world > 1 and self.args.exchange != "none":
             view = self.d_out.view(-1)[: self.MG.padded_height(self.H) * self.W * self.channels].view(
                 self.MG.padded_height(self.H), self.W, self.channels)
             return self.MG.gather_interleaved_bands(view, self.H, self.rank, self.world)
@@ -375,7 +378,7 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
     # CTAs fill the SMs that the previous frame's tail leaves idle.  The timed region starts on `stream` with both
     # streams idle and ends on `stream` after it has joined the others.
     n_flight = max(1, min(4, args.bands_inflight if bands else args.inflight))
-    if bands and job.peer is None:
+    if bands and job.peer is None and not (world > 1 and args.exchange == "none"):
         n_flight = 1                         # the NCCL gather path works on one buffer
     if job.peer is not None:
         n_flight = min(n_flight, len(job.peer.ptrs))     # one stream per rotating buffer
@@ -387,16 +390,19 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
     ev0.record(stream)
     for s2 in streams[1:]:
         s2.wait_event(ev0)
+    t_host0 = time.perf_counter()
     for i, n in enumerate(my_frames):
         if bands:
-            job.render_step(n, stream=streams[i % n_flight], frame=timed_frames[i])
+            job.render_step(n, stream=streams[i % n_flight], frame=timed_frames[i], out=outs[i % n_flight])
         else:
             r.render_device(timed_frames[i], outs[i % n_flight], streams[i % n_flight].cuda_stream)
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3      # the host's share: how long the K enqueues took
     for s2 in streams[1:]:
         stream.wait_stream(s2)
     ev1.record(stream)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
+    dev_ms_own = dev_ms
     keep_busy(0.4)
 
     # ---- e2e: the user's call — host output buffer, D2H inside the timed region ----
@@ -467,14 +473,15 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
     bands_ok = None
     single_ms = None
     if bands and world > 1:
-        gathered = job.render_step(my_frames[0])
+        gathered = job.render_step(my_frames[0], want_tensor=True)
         stream.synchronize()
         if rank == 0:
             whole = torch.zeros_like(job.d_out)
             r.render_device(job.frame_of(my_frames[0], whole=True), whole, stream.cuda_stream)
             stream.synchronize()
             want = whole.view(-1)[: MG.padded_height(H) * W * job.channels].view(MG.padded_height(H), W, job.channels)[:H]
-            bands_ok = bool(torch.equal(gathered, want))
+            # (--exchange none is a diagnostic: the bands stay on their GPUs, there is no gathered frame to compare)
+            bands_ok = bool(torch.equal(gathered, want)) if args.exchange != "none" else None
             # the same frames rendered whole by this one GPU, same build, same two-in-flight pipeline: the strong-scaling base
             k1 = min(len(my_frames), 24)
             outs1 = [whole, torch.zeros_like(whole)]
@@ -501,7 +508,12 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
 
     vals = torch.tensor([dev_ms, e2e_ms, float(S), float(hits), float(fetches), k_ms_mean], dtype=torch.float64,
                         device=f"cuda:{local}")
+    per_rank = None
     if dist is not None:
+        mine = torch.tensor([dev_ms_own, host_enqueue_ms, k_ms_mean], dtype=torch.float64, device=f"cuda:{local}")
+        every = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank = [[float(x) for x in t.tolist()] for t in every]
         mx = vals.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = vals.clone()
@@ -519,7 +531,12 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
         frames_total = steps * (1 if bands else world)
         value = rays_total / (dev_ms * 1e-3) / 1e6
         e2e_value = rays_total / (e2e_ms * 1e-3) / 1e6
-        launches = steps * world
+        launches = steps * world             # render-kernel launches (the roofline's "per launch")
+        # every kernel of ours inside the timed region: the render kernel, plus per frame the one-thread peer-frame
+        # kernels (every rank: wait for the buffer's release + signal arrival; the root: wait for all + release)
+        all_launches = launches
+        if bands and world > 1 and args.exchange in ("peer", "peer-copy"):
+            all_launches += steps * (2 * world + 2)
         # algorithmic bytes: 8 B per reference step + 4 B colormap per hit + 4 B store per pixel
         # (3 B in RGB8), per launch = per rank and frame
         px_bytes = job.channels
@@ -542,6 +559,8 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
             prof = {"dram_bytes": prof}
         traffic = prof.get("dram_bytes")
         warp_inst = prof.get("warp_inst")
+        if bands and world > 1:
+            traffic = warp_inst = None       # the ncu capture is of a whole-frame launch; a band launch was not captured
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
         issue_frac = None
         if warp_inst and world == 1:
@@ -564,7 +583,8 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
                                                     "release through device-side counters in rank 0's memory (no collective)",
                                        "peer-allreduce": "every rank's kernel stores its bands straight into rank 0's frame; "
                                                          "one-element NCCL all-reduce as the completion barrier",
-                                       "gather": "bands packed, gathered to rank 0 (NCCL), unpacked"}[args.exchange]
+                                       "gather": "bands packed, gathered to rank 0 (NCCL), unpacked",
+                                       "none": "DIAGNOSTIC: no exchange, the bands stay on the GPUs that rendered them"}[args.exchange]
                                     if world > 1 else "one GPU renders the whole frame") if bands else
                                    f"frames round-robin over {world} GPU(s), maps replicated, no collective",
                        "l2": "inputs larger than L2 (the height pyramid's level 0 alone is >= 128 MiB; the camera moves "
@@ -600,7 +620,9 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
                     if (bands and world > 1) else "hmrm_render_async + hmrm_wait_pending(3): every frame lands in pinned host memory; the "
                            "copy-out of frame n overlaps the kernels of the next frames (four device + four host "
                            "buffers)"},
-            "gpu_launches": launches,
+            "gpu_launches": all_launches,
+            "render_kernel_launches": launches,
+            "host_enqueue_ms_per_step": host_enqueue_ms / steps,
             "clocks": clocks,
         }
         if bands_ok is not None:
@@ -608,6 +630,10 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
             rec["single_gpu_ms_per_step"] = single_ms
             rec["strong_scaling_efficiency"] = (single_ms / (dev_ms / steps)) / world if single_ms else None
             rec["kernel_ms_per_rank"] = k_ms
+            if per_rank is not None:
+                rec["per_rank"] = {"timed_region_ms_per_step": [x[0] / steps for x in per_rank],
+                                   "host_enqueue_ms_per_step": [x[1] / steps for x in per_rank],
+                                   "render_kernel_alone_ms": [x[2] for x in per_rank]}
         if want_cpu:
             with tempfile.TemporaryDirectory(prefix="hmrm_bench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None) as td:
                 res = run_cpu_reference(wl, my_frames[:args.cpu_frames], 1, Path(td))
@@ -741,8 +767,9 @@ def main() -> None:
                     help="frame format: rgb8 = the reference's pixels without the constant alpha byte (default), "
                          "rgba8 = the reference's framebuf layout")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", choices=["auto", "peer", "peer-copy", "peer-allreduce", "gather"], default="auto",
-                    help="bands workloads at N > 1: how the bands reach rank 0")
+    ap.add_argument("--exchange", choices=["auto", "peer", "peer-copy", "peer-allreduce", "gather", "none"], default="auto",
+                    help="bands workloads at N > 1: how the bands reach rank 0 (none: a diagnostic, the bands stay where "
+                         "they were rendered: the render kernels' own floor)")
     ap.add_argument("--no-bands", action="store_true", help="N > 1: skip the bands8k sub-record")
     ap.add_argument("--bands-workload", choices=["bands8k", "smokebands"], default="bands8k")
     ap.add_argument("--bands-steps", type=int, default=96)

@@ -63,7 +63,7 @@ struct LaunchSlot {
 // Experiment knobs (environment, read ONCE in hmrm_create): they never change a result, only how the work is
 // scheduled / how many fetches are issued.
 struct Knobs {
-	bool no_row_order, no_batch, debug_sched;
+	bool no_row_order, no_batch, debug_sched, reset_memset;
 	int lmin_bias, lstride, lstart, sky_batch;
 	float cell_exit, climb;
 	bool zq_shrink_set;
@@ -326,6 +326,12 @@ int validate_frame(hmrm_ctx *c, const hmrm_frame *f, int *row_begin, int *row_en
 	return HMRM_OK;
 }
 
+// Zeroes a launch slot's tile-queue counter and statistics block (sizeof(DeviceStats) is a multiple of 4).
+__global__ void k_reset_slot(unsigned int *tile_counter, unsigned int *stats_words) {
+	if (threadIdx.x == 0) *tile_counter = 0u;
+	for (unsigned i = threadIdx.x; i < sizeof(DeviceStats) / 4; i += 32) stats_words[i] = 0u;
+}
+
 // Enqueue one frame on `stream`, writing RGBA8 into d_out.
 int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream_t stream, bool timed) {
 	int row_begin = 0, row_end = 0;
@@ -513,8 +519,15 @@ int enqueue_render(hmrm_ctx *c, const hmrm_frame *f, uint32_t *d_out, cudaStream
 	P.stats = slot.d_stats;
 	P.tile_counter = slot.d_tile_counter;
 
-	HMRM_CUDA(c, cudaMemsetAsync(slot.d_tile_counter, 0, sizeof(unsigned int), stream));
-	HMRM_CUDA(c, cudaMemsetAsync(slot.d_stats, 0, sizeof(DeviceStats), stream));
+	if (c->knobs.reset_memset) {
+		HMRM_CUDA(c, cudaMemsetAsync(slot.d_tile_counter, 0, sizeof(unsigned int), stream));
+		HMRM_CUDA(c, cudaMemsetAsync(slot.d_stats, 0, sizeof(DeviceStats), stream));
+	}
+	else {
+		// one tiny kernel instead of two memsets: stays on the compute queue, never behind a frame copy on a copy engine
+		k_reset_slot<<<1, 32, 0, stream>>>(slot.d_tile_counter, (unsigned int *)slot.d_stats);
+		HMRM_CUDA(c, cudaGetLastError());
+	}
 
 	int traversal = f->traversal;
 	if (traversal == HMRM_TRAVERSAL_AUTO) traversal = c->skip_ready ? HMRM_TRAVERSAL_SKIP : HMRM_TRAVERSAL_BRUTE;
@@ -702,6 +715,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 		Knobs &k = c->knobs;
 		const char *e;
 		k.no_row_order = std::getenv("HMRM_NO_ROW_ORDER") != NULL;
+		k.reset_memset = std::getenv("HMRM_RESET_MEMSET") != NULL;
 		k.no_batch = std::getenv("HMRM_NO_BATCH") != NULL;
 		k.debug_sched = std::getenv("HMRM_DEBUG_SCHED") != NULL;
 		k.lmin_bias = (e = std::getenv("HMRM_LMIN_BIAS")) ? std::atoi(e) : 0;
