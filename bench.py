@@ -273,7 +273,7 @@ class Job:
             args.exchange = "peer" if world <= 2 else "peer-copy"
         if self.bands and world > 1 and args.exchange in ("peer", "peer-copy", "peer-allreduce"):
             self.peer = MG.PeerFrame(self.r, self.H, self.W, rank, world, local, channels=self.channels,
-                                     buffers=max(2, min(4, args.bands_inflight)),
+                                     buffers=max(2, min(6, args.bands_inflight)),
                                      completion="allreduce" if args.exchange == "peer-allreduce" else "device",
                                      exchange="copy" if args.exchange == "peer-copy" else "stores")
 
@@ -377,7 +377,7 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
     # Two frames in flight: frames alternate between two streams (and two output buffers) so that the next frame's
     # CTAs fill the SMs that the previous frame's tail leaves idle.  The timed region starts on `stream` with both
     # streams idle and ends on `stream` after it has joined the others.
-    n_flight = max(1, min(4, args.bands_inflight if bands else args.inflight))
+    n_flight = max(1, min(6 if bands else 4, args.bands_inflight if bands else args.inflight))
     if bands and job.peer is None and not (world > 1 and args.exchange == "none"):
         n_flight = 1                         # the NCCL gather path works on one buffer
     if job.peer is not None:
@@ -719,7 +719,8 @@ def ours_arm(args, wl) -> None:
             "scaling": rec["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         }
         for k in ("config", "march_steps_per_s", "ref_steps_per_frame", "fetches_per_frame", "roofline", "e2e", "gpu_launches",
-                  "clocks", "single_gpu_ms_per_step", "strong_scaling_efficiency", "kernel_ms_per_rank", "cpu_baseline"):
+                  "render_kernel_launches", "host_enqueue_ms_per_step", "clocks", "single_gpu_ms_per_step", "strong_scaling_efficiency",
+                  "kernel_ms_per_rank", "per_rank", "cpu_baseline"):
             if k in rec:
                 line[k] = rec[k]
         if sub is not None:
@@ -775,9 +776,9 @@ def main() -> None:
     ap.add_argument("--bands-steps", type=int, default=96)
     ap.add_argument("--cpu-frames", type=int, default=2)
     ap.add_argument("--inflight", type=int, default=2, help="frames in flight in the device-resident timing (1..4)")
-    ap.add_argument("--bands-inflight", type=int, default=3,
-                    help="bands workloads: frames in flight (1..4; one stream and one peer buffer each); measured at N = 4: "
-                         "0.442 ms per 8K frame with 2, 0.411 ms with 3")
+    ap.add_argument("--bands-inflight", type=int, default=4,
+                    help="bands workloads: frames in flight (1..6; one stream and one peer buffer each); measured per 8K frame: "
+                         "N = 4: 0.442 ms with 2, 0.411 ms with 3; N = 8: 0.2395 / 0.2268 / 0.2215 ms with 2 / 3 / 4")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -5,6 +5,7 @@
 // the K1 prepass when lum/min/max/maps change, build the per-frame image-plane
 // constants with the host libm, launch K2, move the framebuffer.
 // There is no CPU rendering path in this library.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -34,7 +35,7 @@ namespace {
 
 std::string g_create_error;
 
-const int kLaunchSlots = 6;
+const int kLaunchSlots = 8;
 const int kFrameRing = 4;      // device frame buffers (and compute streams) whole frames rotate through
 
 // Everything one launch writes before / while its kernel runs.  A slot is reused only after the kernel that used
@@ -63,7 +64,7 @@ struct LaunchSlot {
 // Experiment knobs (environment, read ONCE in hmrm_create): they never change a result, only how the work is
 // scheduled / how many fetches are issued.
 struct Knobs {
-	bool no_row_order, no_batch, debug_sched, reset_memset;
+	bool no_row_order, no_batch, debug_sched, reset_memset, peer_memops;
 	int lmin_bias, lstride, lstart, sky_batch;
 	float cell_exit, climb;
 	bool zq_shrink_set;
@@ -674,6 +675,71 @@ int enqueue_copy_out(hmrm_ctx *c, const hmrm_frame *f, const uint32_t *fb, uint8
 	return HMRM_OK;
 }
 
+// ---- peer-frame synchronisation words: one-thread kernels (default) or stream memory operations -----------------
+// HMRM_PEER_SYNC=memops: the waits and writes of csrc/peer_sync.cuh's protocol are cuStreamWaitValue32 /
+// cuStreamWriteValue32, executed by the GPU's front end.  A one-thread kernel needs a free CTA slot, and the persistent
+// render kernels of the frames in flight hold every slot of the device until their tail: each kernel of the protocol
+// then waits for the next render kernel to drain.  The memory operations need no SM.  (They have no timeout: a
+// missing peer leaves the stream blocked — cudaStreamQuery stays cudaErrorNotReady — instead of raising the error word.)
+typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct MemOps {
+	StreamValueFn wait32, write32;
+	int state;   // 0 = not looked up, 1 = ready, -1 = unavailable
+};
+MemOps g_memops = {NULL, NULL, 0};
+
+int load_memops(hmrm_ctx *c) {
+	if (g_memops.state == 0) {
+		void *w = NULL, *x = NULL;
+		cudaDriverEntryPointQueryResult qw, qx;
+		cudaError_t e1 = cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &qw);
+		cudaError_t e2 = cudaGetDriverEntryPoint("cuStreamWriteValue32", &x, cudaEnableDefault, &qx);
+		if (e1 == cudaSuccess && e2 == cudaSuccess && qw == cudaDriverEntryPointSuccess && qx == cudaDriverEntryPointSuccess && w && x) {
+			g_memops.wait32 = (StreamValueFn)w;
+			g_memops.write32 = (StreamValueFn)x;
+			g_memops.state = 1;
+		}
+		else {
+			cudaGetLastError();
+			g_memops.state = -1;
+		}
+	}
+	if (g_memops.state != 1) return fail(c, HMRM_ERR_CUDA, "HMRM_PEER_SYNC=memops: the driver has no stream memory operations");
+	return HMRM_OK;
+}
+
+int peer_wait_word(hmrm_ctx *c, unsigned int *word, unsigned int target, unsigned int *error, cudaStream_t s) {
+	if (c->knobs.peer_memops) {
+		if (int rc = load_memops(c)) return rc;
+		const CUresult r = g_memops.wait32((CUstream)s, (CUdeviceptr)(uintptr_t)word, target, CU_STREAM_WAIT_VALUE_GEQ);
+		if (r != CUDA_SUCCESS) return fail(c, HMRM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)r);
+		return HMRM_OK;
+	}
+	k_peer_spin<<<1, 1, 0, s>>>(word, target, error, c->knobs.peer_timeout_ns);
+	HMRM_CUDA(c, cudaGetLastError());
+	return HMRM_OK;
+}
+
+int peer_write_word(hmrm_ctx *c, unsigned int *word, unsigned int value, cudaStream_t s) {
+	if (int rc = load_memops(c)) return rc;
+	// default flags: a memory barrier orders everything the stream did before (peer stores, the frame copy) ahead of it
+	const CUresult r = g_memops.write32((CUstream)s, (CUdeviceptr)(uintptr_t)word, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+	if (r != CUDA_SUCCESS) return fail(c, HMRM_ERR_CUDA, "cuStreamWriteValue32 failed (%d)", (int)r);
+	return HMRM_OK;
+}
+
+// this rank's bands of use `use` are in the root's frame
+int peer_arrive(hmrm_ctx *c, PeerCtrl *ctrl, const hmrm_frame *f, unsigned int use, cudaStream_t s) {
+	if (c->knobs.peer_memops) {
+		const int r = f->band_count > 1 ? f->band_index : 0;
+		if (r < 0 || r > 30) return fail(c, HMRM_ERR_INVALID, "peer frame: band_index %d out of range", r);
+		return peer_write_word(c, &ctrl->arrived_by[r], use, s);
+	}
+	k_peer_signal<<<1, 1, 0, s>>>(&ctrl->arrived);
+	HMRM_CUDA(c, cudaGetLastError());
+	return HMRM_OK;
+}
+
 } // namespace
 
 extern "C" {
@@ -716,6 +782,7 @@ int hmrm_create(int device, hmrm_ctx **out) {
 		const char *e;
 		k.no_row_order = std::getenv("HMRM_NO_ROW_ORDER") != NULL;
 		k.reset_memset = std::getenv("HMRM_RESET_MEMSET") != NULL;
+		k.peer_memops = (e = std::getenv("HMRM_PEER_SYNC")) != NULL && std::strcmp(e, "memops") == 0;
 		k.no_batch = std::getenv("HMRM_NO_BATCH") != NULL;
 		k.debug_sched = std::getenv("HMRM_DEBUG_SCHED") != NULL;
 		k.lmin_bias = (e = std::getenv("HMRM_LMIN_BIAS")) ? std::atoi(e) : 0;
@@ -1318,13 +1385,11 @@ int hmrm_render_peer(hmrm_ctx *c, const hmrm_frame *f, void *d_frame, void *d_ct
 	cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
 	PeerCtrl *ctrl = (PeerCtrl *)d_ctrl;
 	// the buffer may be overwritten once the root has read its previous use
-	k_peer_spin<<<1, 1, 0, s>>>(&ctrl->released, use - 1u, &ctrl->error, c->knobs.peer_timeout_ns);
-	HMRM_CUDA(c, cudaGetLastError());
-	const int rc = enqueue_render(c, f, (uint32_t *)d_frame, s, true);
+	int rc = peer_wait_word(c, &ctrl->released, use - 1u, &ctrl->error, s);
 	if (rc) return rc;
-	k_peer_signal<<<1, 1, 0, s>>>(&ctrl->arrived);
-	HMRM_CUDA(c, cudaGetLastError());
-	return HMRM_OK;
+	rc = enqueue_render(c, f, (uint32_t *)d_frame, s, true);
+	if (rc) return rc;
+	return peer_arrive(c, ctrl, f, use, s);
 }
 
 int hmrm_render_peer_staged(hmrm_ctx *c, const hmrm_frame *f, void *d_stage, void *d_frame, void *d_ctrl, uint32_t use,
@@ -1339,33 +1404,36 @@ int hmrm_render_peer_staged(hmrm_ctx *c, const hmrm_frame *f, void *d_stage, voi
 	if (rc) return rc;
 	// ... then, once the root has read the previous use of the shared buffer, push this rank's tile rows over NVLink
 	// with the copy engine: large transfers instead of the kernel's 24- or 32-byte row pieces
-	k_peer_spin<<<1, 1, 0, s>>>(&ctrl->released, use - 1u, &ctrl->error, c->knobs.peer_timeout_ns);
-	HMRM_CUDA(c, cudaGetLastError());
+	rc = peer_wait_word(c, &ctrl->released, use - 1u, &ctrl->error, s);
+	if (rc) return rc;
 	int rb = f->row_begin, re = f->row_end;
 	if (rb == 0 && re == 0) re = f->screen_height;
 	rc = enqueue_copy_out(c, f, (const uint32_t *)d_stage, (uint8_t *)d_frame, rb, re, cudaMemcpyDeviceToDevice, s);
 	if (rc) return rc;
-	k_peer_signal<<<1, 1, 0, s>>>(&ctrl->arrived);
-	HMRM_CUDA(c, cudaGetLastError());
-	return HMRM_OK;
+	return peer_arrive(c, ctrl, f, use, s);
 }
 
 int hmrm_peer_wait(hmrm_ctx *c, void *d_ctrl, uint32_t use, int32_t ranks, void *stream) {
 	if (!c) return HMRM_ERR_INVALID;
-	if (!d_ctrl || use == 0u || ranks < 1) return fail(c, HMRM_ERR_INVALID, "hmrm_peer_wait: bad arguments");
+	if (!d_ctrl || use == 0u || ranks < 1 || ranks > 31) return fail(c, HMRM_ERR_INVALID, "hmrm_peer_wait: bad arguments");
 	HMRM_CUDA(c, cudaSetDevice(c->device));
 	PeerCtrl *ctrl = (PeerCtrl *)d_ctrl;
-	k_peer_spin<<<1, 1, 0, stream ? (cudaStream_t)stream : c->stream>>>(&ctrl->arrived, use * (uint32_t)ranks, &ctrl->error,
-	                                                                     c->knobs.peer_timeout_ns);
-	HMRM_CUDA(c, cudaGetLastError());
-	return HMRM_OK;
+	cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+	if (c->knobs.peer_memops) {
+		for (int r = 0; r < ranks; ++r)
+			if (int rc = peer_wait_word(c, &ctrl->arrived_by[r], use, &ctrl->error, s)) return rc;
+		return HMRM_OK;
+	}
+	return peer_wait_word(c, &ctrl->arrived, use * (uint32_t)ranks, &ctrl->error, s);
 }
 
 int hmrm_peer_release(hmrm_ctx *c, void *d_ctrl, uint32_t use, void *stream) {
 	if (!c) return HMRM_ERR_INVALID;
 	if (!d_ctrl) return fail(c, HMRM_ERR_INVALID, "hmrm_peer_release: bad arguments");
 	HMRM_CUDA(c, cudaSetDevice(c->device));
-	k_peer_release<<<1, 1, 0, stream ? (cudaStream_t)stream : c->stream>>>(&((PeerCtrl *)d_ctrl)->released, use);
+	cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+	if (c->knobs.peer_memops) return peer_write_word(c, &((PeerCtrl *)d_ctrl)->released, use, s);
+	k_peer_release<<<1, 1, 0, s>>>(&((PeerCtrl *)d_ctrl)->released, use);
 	HMRM_CUDA(c, cudaGetLastError());
 	return HMRM_OK;
 }

@@ -43,17 +43,20 @@ def test_bands_stored_into_the_root_frame_equal_the_whole_frame(hmrm, world, com
     assert json.loads(out.read_text()) == [True, True, True, True]
 
 
-def test_device_side_completion_protocol_in_one_stream(hmrm):
+@pytest.mark.parametrize("sync", ["kernels", "memops"])
+def test_device_side_completion_protocol_in_one_stream(hmrm, sync, monkeypatch):
     """hmrm_render_peer / hmrm_peer_wait / hmrm_peer_release (csrc/peer_sync.cuh) with three emulated ranks in ONE
     process and ONE stream: every wait is already satisfied by kernels earlier in the stream, so nothing spins on
     another launch.  Checks the counting (arrived = uses * ranks, released = uses), the frames (RGBA8 and RGB8, two
-    rotating buffers, six frames) and that no wait timed out."""
+    rotating buffers, six frames) and that no wait timed out.  sync = memops: the same protocol through stream memory
+    operations (HMRM_PEER_SYNC, read by hmrm_create): per-rank arrival words instead of the counter."""
     import numpy as np
     import torch
 
     from heightmap_ray_marcher_b200 import multi_gpu as MG
 
     W, H, ranks = 322, 187, 3
+    monkeypatch.setenv("HMRM_PEER_SYNC", sync)
     r = hmrm.Renderer(0)
     try:
         r.min_height, r.max_height = 0.0, 10.0
@@ -83,7 +86,7 @@ def test_device_side_completion_protocol_in_one_stream(hmrm):
                 assert np.array_equal(got, want[..., :channels]), (channels, i)
             stream.synchronize()
             for b in range(2):
-                assert r.peer_status(pf.ctrl(b)) == (3 * ranks, 3, 0)
+                assert r.peer_status(pf.ctrl(b)) == (3 * ranks if sync == "kernels" else 0, 3, 0)
             pf.check()
             pf.close()
     finally:
