@@ -23,11 +23,15 @@ bool decode_tga(const std::vector<uint8_t> &file, Decoded *out, std::string *err
 bool decode_bmp(const std::vector<uint8_t> &file, Decoded *out, std::string *error);
 bool decode_gif(const std::vector<uint8_t> &file, Decoded *out, std::string *error);
 bool decode_psd(const std::vector<uint8_t> &file, Decoded *out, std::string *error);
+bool decode_hdr(const std::vector<uint8_t> &file, Decoded *out, std::string *error);   // tone-mapped to 8 bit like stbi_load
+bool decode_pic(const std::vector<uint8_t> &file, Decoded *out, std::string *error);
 bool decode_jpeg(const std::vector<uint8_t> &file, int want_channels, Image *out, std::string *error);
 
 // Content sniffing in stb's order (stbi__load_main, :1118-1170): tells which loader stb would pick.
 bool looks_like_bmp(const std::vector<uint8_t> &file);
 bool looks_like_tga(const std::vector<uint8_t> &file);
+bool looks_like_hdr(const std::vector<uint8_t> &file);
+bool looks_like_pic(const std::vector<uint8_t> &file);
 
 } // namespace hmrm_host
 

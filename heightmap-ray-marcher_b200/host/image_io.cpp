@@ -269,19 +269,13 @@ bool load_image(const std::string &path, int want_channels, Image *out, std::str
 	else if (looks_like_bmp(file)) ok = decode_bmp(file, &d, &err);
 	else if (n >= 6 && !std::memcmp(file.data(), "GIF8", 4) && (file[4] == '7' || file[4] == '9') && file[5] == 'a') ok = decode_gif(file, &d, &err);
 	else if (n >= 4 && !std::memcmp(file.data(), "8BPS", 4)) ok = decode_psd(file, &d, &err);
-	else if (n >= 92 && !std::memcmp(file.data(), "\x53\x80\xF6\x34", 4) && !std::memcmp(file.data() + 88, "PICT", 4)) {
-		ok = false;
-		err = "Softimage PIC is not supported";
-	}
+	else if (looks_like_pic(file)) ok = decode_pic(file, &d, &err);
 	else if (n >= 2 && file[0] == 0xFF && file[1] == 0xD8) {
 		if (!decode_jpeg(file, want_channels, out, &err)) { *error = err; return false; }
 		return true;
 	}
 	else if (n >= 2 && file[0] == 'P' && (file[1] == '5' || file[1] == '6')) ok = decode_pnm(file, want_channels, &d, &err);
-	else if ((n >= 10 && !std::memcmp(file.data(), "#?RADIANCE", 10)) || (n >= 6 && !std::memcmp(file.data(), "#?RGBE", 6))) {
-		ok = false;
-		err = "Radiance HDR is not supported";
-	}
+	else if (looks_like_hdr(file)) ok = decode_hdr(file, &d, &err);
 	else if (looks_like_tga(file)) ok = decode_tga(file, &d, &err);
 	else { ok = false; err = "unknown image type"; }
 	if (!ok) { *error = err; return false; }

@@ -13,8 +13,10 @@
 //   PSD   composited RGB(A), 8/16 bit, raw or RLE                                          image_formats.cpp
 //   TGA   true colour 15/16/24/32, grey, grey+alpha, colour-mapped, raw or RLE            image_formats.cpp
 //   PNM   binary P5 / P6, 8 bit, and 16 bit where stb's result is defined                 image_formats.cpp
+//   PIC   Softimage: raw, pure and mixed run-length packets, any channel split            image_hdr_pic.cpp
+//   HDR   Radiance RGBE, run-length or flat, tone-mapped to 8 bit as stbi_load does       image_hdr_pic.cpp
 // The format is recognised from the file's content in stb's order (TGA last: it has no signature), not from its name.
-// Not supported (stb_image reads them): Radiance HDR and Softimage PIC; BMP RLE is refused by stb too.
+// That is every format stbi_load reads; BMP RLE is refused by stb too.
 //
 // Conversion rules reproduced (vendor/stb_image.h: stbi__convert_format, stbi__convert_16_to_8,
 // stbi__compute_transparency, stbi__expand_png_palette): grey -> R=G=B; missing alpha -> 255;

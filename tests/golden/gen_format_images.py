@@ -200,4 +200,101 @@ psd(out / "grey_as_rgb_1ch.psd", 1, 8, [grey])
 # ---- PNM 16 bit ----
 v16 = rng.randint(0, 65536, size=(h, w, 3)).astype(">u2")
 (out / "rgb16.ppm").write_bytes(b"P6\n%d %d\n65535\n" % (w, h) + v16.tobytes())
+# ---- Radiance HDR (RGBE) ----
+rng2 = np.random.RandomState(77)
+
+
+def rgbe_pixels(hh, ww):
+    """Random RGBE quadruples: exponents around 128 (values around 0.1 .. 4), some zero exponents, some saturating."""
+    px = rng2.randint(0, 256, size=(hh, ww, 4)).astype(np.uint8)
+    px[..., 3] = rng2.randint(120, 132, size=(hh, ww))
+    px[::4, ::3, 3] = 0              # exponent 0: black whatever the mantissas say
+    px[1::5, 1::4, 3] = 140          # far above 1.0: clamps to 255
+    px[..., 0] |= 0x80               # a normalised pixel has one mantissa >= 128: never mistaken for an RLE marker
+    return px
+
+
+def hdr_rle_rows(px):
+    """The 'new' run-length scanlines: 2 2 hi lo, then each of the four components run-length coded."""
+    data = b""
+    for row in px:
+        data += bytes([2, 2, row.shape[0] >> 8, row.shape[0] & 255])
+        for k in range(4):
+            comp, i = row[:, k].tolist(), 0
+            while i < len(comp):
+                j = i
+                while j + 1 < len(comp) and comp[j + 1] == comp[i] and j - i < 126:
+                    j += 1
+                if j - i >= 2:
+                    data += bytes([128 + (j - i + 1), comp[i]])
+                    i = j + 1
+                else:
+                    k2 = i
+                    while k2 + 1 < len(comp) and k2 - i < 127 and not (k2 + 2 < len(comp) and comp[k2 + 1] == comp[k2 + 2]):
+                        k2 += 1
+                    data += bytes([k2 - i + 1]) + bytes(comp[i:k2 + 1])
+                    i = k2 + 1
+    return data
+
+
+def hdr(path, px, body, magic=b"#?RADIANCE", extra=b"# made by hand\nEXPOSURE=1.0\n"):
+    hh, ww = px.shape[:2]
+    path.write_bytes(magic + b"\n" + extra + b"FORMAT=32-bit_rle_rgbe\n\n-Y %d +X %d\n" % (hh, ww) + body)
+
+
+e = rgbe_pixels(h, w)
+e[:, 5:12, :3] = e[:, 5:6, :3]       # runs
+hdr(out / "rle.hdr", e, hdr_rle_rows(e))
+hdr(out / "rgbe_magic_rle.hdr", e[:6], hdr_rle_rows(e[:6]), magic=b"#?RGBE", extra=b"")
+hdr(out / "flat_wide.hdr", e, e.tobytes())                       # width >= 8 but stored flat
+small = rgbe_pixels(9, 5)
+hdr(out / "flat_narrow.hdr", small, small.tobytes())             # width < 8: always flat
+# a run-length first scanline followed by flat data: the reference restarts at pixel 0 with those four bytes
+mixed = hdr_rle_rows(e[:1]) + np.ascontiguousarray(e[::-1]).tobytes()     # (so the image is e upside down)
+hdr(out / "rle_then_flat.hdr", e, mixed)
+
+# ---- Softimage PIC ----
+
+
+def pic(path, ww, hh, packets, rows):
+    """packets: [(type, channel mask)], rows: per scanline the bytes of each packet in turn."""
+    head = b"\x53\x80\xF6\x34" + struct.pack(">f", 3.71) + b"hand made".ljust(80, b"\0") + b"PICT"
+    head += struct.pack(">HHfHH", ww, hh, 1.0, 3, 0)
+    for i, (t, c) in enumerate(packets):
+        head += bytes([1 if i + 1 < len(packets) else 0, 8, t, c])
+    path.write_bytes(head + b"".join(rows))
+
+
+def pic_mixed(vals):
+    """Mixed run-length coding of a list of per-pixel byte tuples."""
+    data, i = b"", 0
+    while i < len(vals):
+        j = i
+        while j + 1 < len(vals) and vals[j + 1] == vals[i]:
+            j += 1
+        n = j - i + 1
+        if n >= 130:
+            data += bytes([128]) + struct.pack(">H", n) + bytes(vals[i])
+            i = j + 1
+        elif n >= 2:
+            data += bytes([n + 127]) + bytes(vals[i])
+            i = j + 1
+        else:
+            k2 = i
+            while k2 + 1 < len(vals) and k2 - i < 127 and not (k2 + 2 < len(vals) and vals[k2 + 1] == vals[k2 + 2]):
+                k2 += 1
+            data += bytes([k2 - i]) + b"".join(bytes(v) for v in vals[i:k2 + 1])
+            i = k2 + 1
+    return data
+
+
+pic(out / "rgb_raw.pic", w, h, [(0, 0xE0)], [r.tobytes() for r in rgb])
+pic(out / "rgb_plus_alpha_raw.pic", w, h, [(0, 0xE0), (0, 0x10)], [rgba[y, :, :3].tobytes() + rgba[y, :, 3].tobytes() for y in range(h)])
+wide = np.repeat(flat[:, :, :], 16, axis=1)[:, :300]             # long runs: the 16-bit repeat count
+wide[:, 40:45] = rng2.randint(0, 256, size=(h, 5, 3))
+pic(out / "rgb_mixed_rle.pic", 300, h, [(2, 0xE0)], [pic_mixed([tuple(p) for p in r.tolist()]) for r in wide])
+row_pure = [b"".join(bytes([4]) + bytes(r[x0].tolist()) for x0 in range(0, 20, 4)) for r in rgb]      # last run clipped at the width
+pic(out / "rgb_pure_rle.pic", w, h, [(1, 0xE0)], row_pure)
+pic(out / "red_blue_only_mixed.pic", w, h, [(2, 0xA0)],
+    [pic_mixed([(p[0], p[2]) for p in r.tolist()]) for r in flat])
 print(len(list(out.iterdir())), "images")

@@ -136,6 +136,7 @@ CONFIGS = {
     # the reference's own sample_config.txt names JPEG maps ("heightmap path/to/img.jpg")
     "jpeg_maps": "heightmap grey.jpg colormap base_444.jpg resolution 32 18\n",
     "bmp_gif_maps": "heightmap rgb24.bmp colormap transparent.gif\n",
+    "hdr_pic_maps": "heightmap rle.hdr colormap rgb_plus_alpha_raw.pic\n",
 }
 
 
