@@ -8,8 +8,8 @@
 //   every rank, use u of a buffer:   k_peer_spin(released >= u - 1)  ->  render kernel  ->  k_peer_signal(arrived += 1)
 //   root:                            ... -> k_peer_spin(arrived >= u * ranks) -> [reads the frame] -> k_peer_release(u)
 //
-// (Second implementation of the same protocol, HMRM_PEER_SYNC=memops: cuStreamWaitValue32 / cuStreamWriteValue32 on
-// the same block — the GPU's front end does the waiting and the writing, no SM is involved; see hmrm_api.cu.)
+// (These kernels are the HMRM_PEER_SYNC=kernels implementation.  The default one does the same waits and writes on
+// the same block with cuStreamWaitValue32 / cuStreamWriteValue32 — the GPU's front end, no SM; see hmrm_api.cu.)
 // `arrived` only grows (one increment per rank and use), `released` is the last use the root is done with: a rank may
 // overwrite the buffer for use u only when use u - 1 has been read.  No host synchronisation, no collective.
 // A wait that does not end within the timeout raises the block's error word and lets the stream continue, so that a
