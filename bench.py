@@ -249,6 +249,10 @@ def reference_arm(args, wl) -> None:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+PEER_SYNC_TEXT = {"memops": "waited on and written by stream memory operations (the GPU front end, no SM)",
+                  "kernels": "polled and written by one-thread kernels"}
+
+
 class Job:
     """One workload on this rank: renderer, frames, output buffers."""
 
@@ -532,10 +536,11 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
         value = rays_total / (dev_ms * 1e-3) / 1e6
         e2e_value = rays_total / (e2e_ms * 1e-3) / 1e6
         launches = steps * world             # render-kernel launches (the roofline's "per launch")
-        # every kernel of ours inside the timed region: the render kernel, plus per frame the one-thread peer-frame
-        # kernels (every rank: wait for the buffer's release + signal arrival; the root: wait for all + release)
+        # every kernel of ours inside the timed region: the render kernel, plus — only when the peer-frame protocol
+        # runs as one-thread kernels (HMRM_PEER_SYNC=kernels; the default are stream memory operations, no kernels) —
+        # per frame: every rank waits for the buffer's release and signals arrival, the root waits for all and releases
         all_launches = launches
-        if bands and world > 1 and args.exchange in ("peer", "peer-copy"):
+        if bands and world > 1 and args.exchange in ("peer", "peer-copy") and r.peer_sync_mode() == "kernels":
             all_launches += steps * (2 * world + 2)
         # algorithmic bytes: 8 B per reference step + 4 B colormap per hit + 4 B store per pixel
         # (3 B in RGB8), per launch = per rank and frame
@@ -575,12 +580,13 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
                        "in_flight": f"{n_flight} frame(s) on as many streams (the tail of frame n overlaps the head of frame n+1)",
                        "sharding": (f"each frame split into interleaved 4-row tile bands over {world} GPU(s), maps replicated; "
                                     + {"peer": "every rank's kernel stores its bands straight into rank 0's frame (CUDA IPC peer "
-                                               "memory over NVLink); completion and buffer release through device-side counters "
-                                               "in rank 0's memory (no collective)",
+                                               "memory over NVLink); completion and buffer release through words in rank 0's "
+                                               "memory, " + PEER_SYNC_TEXT[r.peer_sync_mode()] + " (no collective)",
                                        "peer-copy": "every rank renders its bands into a staging frame on its own device and pushes "
                                                     "its tile rows into rank 0's frame with one strided device-to-device copy "
                                                     "(CUDA IPC peer memory over NVLink, copy engine); completion and buffer "
-                                                    "release through device-side counters in rank 0's memory (no collective)",
+                                                    "release through words in rank 0's memory, "
+                                                    + PEER_SYNC_TEXT[r.peer_sync_mode()] + " (no collective)",
                                        "peer-allreduce": "every rank's kernel stores its bands straight into rank 0's frame; "
                                                          "one-element NCCL all-reduce as the completion barrier",
                                        "gather": "bands packed, gathered to rank 0 (NCCL), unpacked",

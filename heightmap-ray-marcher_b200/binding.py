@@ -118,6 +118,7 @@ PROTOTYPES = {
     "hmrm_peer_wait": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p]),
     "hmrm_peer_release": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
     "hmrm_peer_status": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint32)]),
+    "hmrm_peer_sync_mode": (C.c_int, [C.c_void_p]),
     "hmrm_debug_aabb": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
@@ -380,6 +381,10 @@ class Renderer:
 
     def peer_release(self, d_ctrl: int, use: int, stream=None) -> None:
         self._check(self._lib.hmrm_peer_release(self._h, C.c_void_p(d_ctrl), use, _ptr(stream)))
+
+    def peer_sync_mode(self) -> str:
+        """Which implementation of the peer-frame protocol this context uses: "memops" or "kernels"."""
+        return "memops" if self._lib.hmrm_peer_sync_mode(self._h) == 1 else "kernels"
 
     def peer_status(self, d_ctrl: int):
         out = (C.c_uint32 * 3)()

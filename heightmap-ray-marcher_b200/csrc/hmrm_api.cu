@@ -1464,6 +1464,11 @@ int hmrm_peer_status(hmrm_ctx *c, void *d_ctrl, uint32_t out[3]) {
 	return HMRM_OK;
 }
 
+int hmrm_peer_sync_mode(const hmrm_ctx *c) {
+	if (!c) return -HMRM_ERR_INVALID;
+	return c->knobs.peer_memops ? HMRM_PEER_SYNC_MEMOPS : HMRM_PEER_SYNC_KERNELS;
+}
+
 int hmrm_ipc_close(hmrm_ctx *c, void *dptr) {
 	if (!c) return HMRM_ERR_INVALID;
 	HMRM_CUDA(c, cudaSetDevice(c->device));

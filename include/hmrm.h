@@ -232,6 +232,9 @@ int hmrm_render_peer_staged(hmrm_ctx *ctx, const hmrm_frame *f, void *d_stage, v
 int hmrm_peer_wait(hmrm_ctx *ctx, void *d_ctrl, uint32_t use, int32_t ranks, void *stream);
 int hmrm_peer_release(hmrm_ctx *ctx, void *d_ctrl, uint32_t use, void *stream);
 int hmrm_peer_status(hmrm_ctx *ctx, void *d_ctrl, uint32_t out[3]);
+#define HMRM_PEER_SYNC_KERNELS 0
+#define HMRM_PEER_SYNC_MEMOPS 1
+int hmrm_peer_sync_mode(const hmrm_ctx *ctx);     /* which implementation this context uses; < 0: ctx is NULL */
 
 #ifdef __cplusplus
 }
