@@ -41,7 +41,7 @@ def build_hmap(force: bool = False) -> Path:
     newest = max(p.stat().st_mtime for p in list(HOST.glob("*")) + [PKG.parent / "include" / "hmrm.h", LIB])
     if not force and HMAP.exists() and HMAP.stat().st_mtime >= newest:
         return HMAP
-    cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-ffp-contract=off", "-o", str(HMAP), *[str(s) for s in srcs],
+    cmd = ["g++", "-std=c++11", "-O2", "-Wall", "-Wextra", "-ffp-contract=off", "-fwrapv", "-o", str(HMAP), *[str(s) for s in srcs],
            "-L", str(PKG), "-lhmrm", "-lz", "-pthread", "-Wl,-rpath,$ORIGIN"]
     subprocess.run(cmd, check=True, cwd=str(PKG))
     return HMAP

@@ -257,9 +257,14 @@ bool decode_png(const std::vector<uint8_t> &file, Decoded *out, std::string *err
 // binary PNM (P5 / P6, maxval <= 255; samples are taken as they are, like stb_image)
 bool load_image(const std::string &path, int want_channels, Image *out, std::string *error) {
 	std::vector<uint8_t> file;
-	std::string err;
 	if (want_channels != 3 && want_channels != 4) { *error = "want_channels must be 3 or 4"; return false; }
 	if (!read_file(path, &file)) { *error = "cannot read file"; return false; }
+	return load_image_memory(file, want_channels, out, error);
+}
+
+bool load_image_memory(const std::vector<uint8_t> &file, int want_channels, Image *out, std::string *error) {
+	std::string err;
+	if (want_channels != 3 && want_channels != 4) { *error = "want_channels must be 3 or 4"; return false; }
 	// Format by content, in the order stb tries its loaders (vendor/stb_image.h stbi__load_main :1118-1170):
 	// PNG, BMP, GIF, PSD, PIC, JPEG, PNM, HDR, and TGA last because it has no signature.
 	Decoded d;

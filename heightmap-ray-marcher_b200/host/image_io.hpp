@@ -41,6 +41,8 @@ struct Image {
 // Decode `path` into 8-bit pixels with `want_channels` (3 = RGB, 4 = RGBA).  Returns false and a
 // message in `error` on failure.
 bool load_image(const std::string &path, int want_channels, Image *out, std::string *error);
+// The same on a file already in memory (stbi_load_from_memory's role).
+bool load_image_memory(const std::vector<uint8_t> &file, int want_channels, Image *out, std::string *error);
 
 // RGBA8 (or RGB8) -> PNG file.  Returns false on failure.
 bool write_png(const std::string &path, int width, int height, int channels, const uint8_t *pixels,
