@@ -107,8 +107,12 @@ ParseStatus consume_config_stream(std::istream &input, Config &c, std::ostream &
 		bool handled = false;
 		for (size_t i = 0; i < sizeof kScalars / sizeof kScalars[0] && !handled; ++i) {
 			if (id != kScalars[i].id) continue;
-			double v;
-			input >> v;      // a malformed number stores 0 and ends parsing at the next token read, as in the reference
+			// A malformed number stores 0 and ends parsing at the next token read, as in the reference; a missing one (end
+			// of the text) leaves the value alone: the reference extracts straight into its global.  (Its three angles
+			// go through an uninitialised local, :367-384, and are indeterminate in that case; here they stay as well.)
+			double v = c.*(kScalars[i].field);
+			if (kScalars[i].degrees) v = rads_to_degrees(v);
+			input >> v;
 			c.*(kScalars[i].field) = kScalars[i].degrees ? degrees_to_rads(v) : v;
 			if (kScalars[i].touches_heights) c.should_update_heightmap = true;
 			echo(c, id, out);
@@ -161,7 +165,9 @@ ParseStatus consume_config_stream(std::istream &input, Config &c, std::ostream &
 			echo(c, "lum", out);
 		}
 		else if (id == "bg_color") {
-			int r, g, b;
+			// The reference reads into three uninitialised ints (:456-457): when an extraction fails it stores 0 and the
+			// components after it are indeterminate there.  Here they keep their current values.
+			int r = c.bg_r, g = c.bg_g, b = c.bg_b;
 			input >> r >> g >> b;
 			c.bg_r = (unsigned char)r;
 			c.bg_g = (unsigned char)g;
