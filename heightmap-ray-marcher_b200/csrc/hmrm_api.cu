@@ -677,50 +677,47 @@ int enqueue_copy_out(hmrm_ctx *c, const hmrm_frame *f, const uint32_t *fb, uint8
 	return HMRM_OK;
 }
 
-// ---- peer-frame synchronisation words: one-thread kernels (default) or stream memory operations -----------------
-// HMRM_PEER_SYNC=memops: the waits and writes of csrc/peer_sync.cuh's protocol are cuStreamWaitValue32 /
-// cuStreamWriteValue32, executed by the GPU's front end.  A one-thread kernel needs a free CTA slot, and the persistent
-// render kernels of the frames in flight hold every slot of the device until their tail: each kernel of the protocol
-// then waits for the next render kernel to drain.  The memory operations need no SM.  (They have no timeout: a
-// missing peer leaves the stream blocked — cudaStreamQuery stays cudaErrorNotReady — instead of raising the error word.)
+// ---- peer-frame synchronisation words: stream memory operations (default) or one-thread kernels ------------------
+// The waits and writes of csrc/peer_sync.cuh's protocol as cuStreamWaitValue32 / cuStreamWriteValue32, executed by the
+// GPU's front end.  A one-thread kernel needs a free CTA slot, and the persistent render kernels of the frames in
+// flight hold every slot of the device until their tail: each kernel of the protocol then waits for the next render
+// kernel to drain.  The memory operations need no SM.  (They have no timeout: a missing peer leaves the stream
+// blocked — cudaStreamQuery stays cudaErrorNotReady — instead of raising the error word.)
 typedef CUresult (*StreamValueFn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 struct MemOps {
-	StreamValueFn wait32, write32;
-	int state;   // 0 = not looked up, 1 = ready, -1 = unavailable
+	StreamValueFn wait32, write32;   // both NULL: the driver does not have them
 };
-MemOps g_memops = {NULL, NULL, 0};
 
-bool probe_memops();
-
-int load_memops(hmrm_ctx *c) {
-	if (g_memops.state == 0) probe_memops();
-	if (g_memops.state != 1) return fail(c, HMRM_ERR_CUDA, "HMRM_PEER_SYNC=memops: the driver has no stream memory operations");
-	return HMRM_OK;
+MemOps lookup_memops() {
+	MemOps m = {NULL, NULL};
+	void *w = NULL, *x = NULL;
+	cudaDriverEntryPointQueryResult qw, qx;
+	const cudaError_t e1 = cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &qw);
+	const cudaError_t e2 = cudaGetDriverEntryPoint("cuStreamWriteValue32", &x, cudaEnableDefault, &qx);
+	if (e1 == cudaSuccess && e2 == cudaSuccess && qw == cudaDriverEntryPointSuccess && qx == cudaDriverEntryPointSuccess && w && x) {
+		m.wait32 = (StreamValueFn)w;
+		m.write32 = (StreamValueFn)x;
+	}
+	else cudaGetLastError();
+	return m;
 }
 
-bool probe_memops() {
-	if (g_memops.state == 0) {
-		void *w = NULL, *x = NULL;
-		cudaDriverEntryPointQueryResult qw, qx;
-		cudaError_t e1 = cudaGetDriverEntryPoint("cuStreamWaitValue32", &w, cudaEnableDefault, &qw);
-		cudaError_t e2 = cudaGetDriverEntryPoint("cuStreamWriteValue32", &x, cudaEnableDefault, &qx);
-		if (e1 == cudaSuccess && e2 == cudaSuccess && qw == cudaDriverEntryPointSuccess && qx == cudaDriverEntryPointSuccess && w && x) {
-			g_memops.wait32 = (StreamValueFn)w;
-			g_memops.write32 = (StreamValueFn)x;
-			g_memops.state = 1;
-		}
-		else {
-			cudaGetLastError();
-			g_memops.state = -1;
-		}
-	}
-	return g_memops.state == 1;
+const MemOps &memops() {
+	static const MemOps m = lookup_memops();   // looked up once (thread-safe), after a device has been selected
+	return m;
+}
+
+bool probe_memops() { return memops().wait32 != NULL; }
+
+int load_memops(hmrm_ctx *c) {
+	if (!probe_memops()) return fail(c, HMRM_ERR_CUDA, "HMRM_PEER_SYNC=memops: the driver has no stream memory operations");
+	return HMRM_OK;
 }
 
 int peer_wait_word(hmrm_ctx *c, unsigned int *word, unsigned int target, unsigned int *error, cudaStream_t s) {
 	if (c->knobs.peer_memops) {
 		if (int rc = load_memops(c)) return rc;
-		const CUresult r = g_memops.wait32((CUstream)s, (CUdeviceptr)(uintptr_t)word, target, CU_STREAM_WAIT_VALUE_GEQ);
+		const CUresult r = memops().wait32((CUstream)s, (CUdeviceptr)(uintptr_t)word, target, CU_STREAM_WAIT_VALUE_GEQ);
 		if (r != CUDA_SUCCESS) return fail(c, HMRM_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)r);
 		return HMRM_OK;
 	}
@@ -732,7 +729,7 @@ int peer_wait_word(hmrm_ctx *c, unsigned int *word, unsigned int target, unsigne
 int peer_write_word(hmrm_ctx *c, unsigned int *word, unsigned int value, cudaStream_t s) {
 	if (int rc = load_memops(c)) return rc;
 	// default flags: a memory barrier orders everything the stream did before (peer stores, the frame copy) ahead of it
-	const CUresult r = g_memops.write32((CUstream)s, (CUdeviceptr)(uintptr_t)word, value, CU_STREAM_WRITE_VALUE_DEFAULT);
+	const CUresult r = memops().write32((CUstream)s, (CUdeviceptr)(uintptr_t)word, value, CU_STREAM_WRITE_VALUE_DEFAULT);
 	if (r != CUDA_SUCCESS) return fail(c, HMRM_ERR_CUDA, "cuStreamWriteValue32 failed (%d)", (int)r);
 	return HMRM_OK;
 }
