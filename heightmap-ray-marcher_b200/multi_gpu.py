@@ -102,9 +102,10 @@ class PeerFrame:
     device-to-device copy (large NVLink transfers; wins when many ranks write into one root).  The root always renders
     straight into its own frame.
 
-    completion = "device" (default): the ranks tell the root "my bands are in" through a counter in the root's memory
-    and the root tells them "buffer read" through another (csrc/peer_sync.cuh) — stream-ordered one-thread kernels, no
-    collective, no host synchronisation.  completion = "allreduce": round 1's one-element all-reduce as the barrier
+    completion = "device" (default): the ranks tell the root "my bands are in" through words in the root's memory and
+    the root tells them "buffer read" through another — stream memory operations executed by the GPU front ends (or
+    one-thread kernels, HMRM_PEER_SYNC=kernels: csrc/peer_sync.cuh), stream-ordered, no collective, no host
+    synchronisation.  completion = "allreduce": round 1's one-element all-reduce as the barrier
     (kept for the A/B and for backends without peer atomics).
 
     `buffers` frames rotate, so frame i + 1 may be rendered while the root still reads frame i:
