@@ -565,10 +565,13 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
         traffic = prof.get("dram_bytes")
         warp_inst = prof.get("warp_inst")
         if bands and world > 1:
-            traffic = warp_inst = None       # the ncu capture is of a whole-frame launch; a band launch was not captured
+            # a band launch: its own capture (rank 0's band of an N-way split, tools/r02_session27.sh), if there is one
+            prof = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(f"{args_workload_key(job)}x{world}", {}) \
+                if (ROOT / "profiles" / "traffic.json").exists() else {}
+            traffic, warp_inst = prof.get("dram_bytes"), prof.get("warp_inst")
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
         issue_frac = None
-        if warp_inst and world == 1:
+        if warp_inst and (world == 1 or bands):
             issue_frac = warp_inst / (SM_COUNT_FALLBACK * 4 * sm_mhz * 1e6 * (k_ms * 1e-3))
         rec = {
             "value": value, "ms_per_step": dev_ms / steps, "steps": steps,

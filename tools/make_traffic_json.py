@@ -17,9 +17,12 @@ ROOT = Path(__file__).resolve().parent.parent
 ap = argparse.ArgumentParser()
 ap.add_argument("csvs", nargs="+")
 ap.add_argument("--note", default="")
+ap.add_argument("--merge", action="store_true", help="add to / replace entries of the existing profiles/traffic.json")
 args = ap.parse_args()
 
 out = {}
+if args.merge:
+    out = json.loads((ROOT / "profiles" / "traffic.json").read_text())
 for path in args.csvs:
     m = re.search(r"_([a-z0-9]+)\.csv$", path)
     workload = m.group(1)
@@ -47,6 +50,8 @@ for path in args.csvs:
         "launches_averaged": len(use),
         "source": path,
     }
+if args.merge and "_note" in out and not args.note:
+    args.note = out["_note"]
 out["_note"] = args.note or "ncu --metrics (clock control none), tools/profile_frame.py, one launch of the render kernel per workload"
 (ROOT / "profiles" / "traffic.json").write_text(json.dumps(out, indent=1) + "\n")
 print(json.dumps(out, indent=1))

@@ -20,6 +20,7 @@ ap.add_argument("--fast", action="store_true", help="HMRM_FP32_FAST")
 ap.add_argument("--vang", type=float, default=None, help="override vang (degrees), e.g. 30 = all sky")
 ap.add_argument("--layout", choices=["rowmajor", "tile4", "zorder"], default=None, help="pyramid layout (default: the library's)")
 ap.add_argument("--rgb8", action="store_true")
+ap.add_argument("--band", default=None, help="N:I = render only rank I's interleaved tile rows of an N-way band split")
 args = ap.parse_args()
 
 hmrm = hmrm_pkg.load()
@@ -29,6 +30,7 @@ r.min_height, r.max_height = bench.MIN_HEIGHT, bench.MAX_HEIGHT
 if args.layout:
     r.set_layout({"rowmajor": 0, "tile4": 1, "zorder": 2}[args.layout])
 r.synth_maps(wl["log2n"], bench.SEED)
+band_count, band_index = (int(v) for v in args.band.split(":")) if args.band else (0, 0)
 trav = {"auto": 0, "brute": 1, "skip": 2, "skip_fp64": 3, "pack": 4}[args.traversal]
 for i in range(args.frames):
     c = bench.camera(wl, args.first + i)
@@ -37,7 +39,8 @@ for i in range(args.frames):
     f = r.frame(projection=wl["projection"], screen_width=wl["W"], screen_height=wl["H"], cam_pos=c["pos"],
                 hang=hmrm.deg2rad(c["hang_deg"]), vang=hmrm.deg2rad(c["vang_deg"]), hfov=hmrm.deg2rad(c["hfov_deg"]),
                 ortho_width=c["ortho_width"], grid_width=bench.GRID_WIDTH, step_dist=wl["step_dist"], traversal=trav, precision=1 if args.fast else 0,
-                flags=hmrm.FLAG_STATS if args.stats else 0, pixel_format=1 if args.rgb8 else 0)
+                flags=hmrm.FLAG_STATS if args.stats else 0, pixel_format=1 if args.rgb8 else 0,
+                band_count=band_count, band_index=band_index)
     out = r.render(f)
     st = r.stats()
     print(f"frame {args.first + i}: kernel {st.kernel_ms:.3f} ms" +
