@@ -555,20 +555,9 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
         except OSError:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        prof = {}
-        try:
-            prof = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(args_workload_key(job), {})
-        except (OSError, ValueError):
-            pass
-        if not isinstance(prof, dict):
-            prof = {"dram_bytes": prof}
+        prof = traffic_profile(args_workload_key(job), bands, world)
         traffic = prof.get("dram_bytes")
         warp_inst = prof.get("warp_inst")
-        if bands and world > 1:
-            # a band launch: its own capture (rank 0's band of an N-way split, tools/r02_session27.sh), if there is one
-            prof = json.loads((ROOT / "profiles" / "traffic.json").read_text()).get(f"{args_workload_key(job)}x{world}", {}) \
-                if (ROOT / "profiles" / "traffic.json").exists() else {}
-            traffic, warp_inst = prof.get("dram_bytes"), prof.get("warp_inst")
         sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz") or 1965.0
         issue_frac = None
         if warp_inst and (world == 1 or bands):
@@ -673,6 +662,17 @@ def measure(job: Job, steps: int, warmup: int, sampler, want_cpu: bool) -> dict 
             if not ok_host:
                 raise SystemExit("bands e2e: the shared host frame differs from the frame rendered whole")
     return rec
+
+
+def traffic_profile(workload: str, bands: bool, world: int) -> dict:
+    """ncu counters of ONE render-kernel launch of this workload (profiles/traffic.json, tools/make_traffic_json.py).
+    A band launch at N > 1 has its own capture (`<workload>x<N>`: rank 0's band of an N-way split) or none."""
+    try:
+        table = json.loads((ROOT / "profiles" / "traffic.json").read_text())
+    except (OSError, ValueError):
+        return {}
+    prof = table.get(f"{workload}x{world}" if (bands and world > 1) else workload, {})
+    return prof if isinstance(prof, dict) else {"dram_bytes": prof}
 
 
 def args_workload_key(job: Job) -> str:

@@ -46,3 +46,17 @@ def test_orbit_camera_stays_outside_the_box():
             assert not inside, (name, n, c)
             # (sample720 is the reference's own default camera: beside the map at z = 0, main/hmap.cpp:75)
             assert z > bench.MAX_HEIGHT or wl.get("camera") == "sample"
+
+
+def test_traffic_profile_lookup():
+    """roofline.traffic comes from profiles/traffic.json: whole-frame launches by workload, band launches of an N-way
+    split by `<workload>x<N>`; a split that was never captured has no traffic figure rather than a wrong one."""
+    import bench
+
+    whole = bench.traffic_profile("bands8k", True, 1)
+    assert whole["dram_bytes"] > 0 and whole["warp_inst"] > 0
+    assert bench.traffic_profile("flythrough4k", False, 8) == bench.traffic_profile("flythrough4k", False, 1)
+    band = bench.traffic_profile("bands8k", True, 8)
+    assert 0 < band["warp_inst"] < whole["warp_inst"] / 7 and band["dram_bytes"] < whole["dram_bytes"]
+    assert bench.traffic_profile("bands8k", True, 3) == {}
+    assert bench.traffic_profile("no_such_workload", False, 1) == {}
