@@ -64,3 +64,12 @@ def test_product_does_not_reference_oracle():
             text = path.read_text()
             for token in ("oracle/", "oracle_", "liboracle", "hmap_oracle", "import oracle"):
                 assert token not in text, f"{path} refers to the oracle ({token})"
+
+
+def test_null_context_is_an_error_not_a_crash(hmrm):
+    """Entry points that take a context refuse NULL with a status (no GPU needed): the C ABI never dereferences it."""
+    lib = hmrm.load_library()
+    assert lib.hmrm_peer_sync_mode(None) < 0
+    assert lib.hmrm_wait(None) != 0
+    assert lib.hmrm_peer_release(None, None, 1, None) != 0
+    lib.hmrm_get_layout(None)          # a plain getter: any value, no crash
