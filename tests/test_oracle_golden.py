@@ -111,3 +111,36 @@ def test_reference_scripted_flythrough_matches_oracle(oracle, tmp_path):
         sc = dict(scene, **s)
         fb, _, _ = H.oracle_render_scene(oracle, sc, (hm, cm))
         assert np.array_equal(got, fb)
+
+
+def random_scene(rng, i):
+    """A random small scene: any projection, camera anywhere around (or inside, or below) the box, any look direction,
+    random luminance weights / height range / step / background."""
+    maps = [S.SYNTH8, S.NOISE, S.CROP][i % 3]
+    extent = 2.56 if maps is S.SYNTH8 else 2.0
+    lo = float(rng.uniform(-1.0, 1.0))
+    return S._scene(f"random_{i}", 1 + i % 3, maps, width=int(rng.integers(24, 97)), height=int(rng.integers(16, 55)),
+                    pos=(float(rng.uniform(-1.5, extent + 1.5)), float(rng.uniform(-extent - 1.5, 1.5)), float(rng.uniform(-1.0, 5.0))),
+                    hang_deg=float(rng.uniform(-180.0, 180.0)), vang_deg=float(rng.uniform(5.0, 175.0)),
+                    hfov_deg=float(rng.uniform(20.0, 150.0)), grid_width=float(rng.choice([0.01, 0.013, 0.02])),
+                    step_dist=float(rng.choice([0.05, 0.02, 0.004, 0.11])), ortho_width=float(rng.uniform(0.005, 0.05)),
+                    min_height=lo, max_height=lo + float(rng.uniform(0.2, 3.0)),
+                    lum=tuple(float(v) for v in rng.uniform(-0.3, 1.2, size=3)), bg=tuple(int(v) for v in rng.integers(0, 256, size=3)))
+
+
+def test_oracle_matches_live_reference_on_random_scenes(oracle, tmp_path):
+    """The restatement against the unmodified reference, rendered now (only where oracle/_ref is built): 18 random
+    scenes beyond the committed golden frames."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    rng = np.random.default_rng(424242)
+    for i in range(18):
+        scene = random_scene(rng, i)
+        hm, cm = H.load_scene_maps(scene, oracle)
+        oracle.write_png(tmp_path / "h.png", hm)
+        oracle.write_png(tmp_path / "c.png", cm)
+        kw = S.frame_kwargs(scene)
+        cfg = oracle.config_text(kw, tmp_path / "h.png", tmp_path / "c.png", lum=scene["lum"])
+        frames, _ = oracle.run_ref(cfg, scene["projection"], kw["width"], kw["height"], binary=oracle.REF_BIN_O2)
+        fb, _, _ = H.oracle_render_scene(oracle, scene, (hm, cm))
+        assert np.array_equal(frames[0], fb), scene
